@@ -1,0 +1,220 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Everything is fp32, produced by the reference's own
+``PysicsInformedNeuralNetwork`` methods (``fwd_computing_loss_2d`` + ``loss.backward()`` +
+``torch.optim.Adam``) on fixed seeds.  The ev solver's constructor hard-requires CUDA
+(ev-NSFnet/pinn_solver.py:62-63), so on CPU the object is built with ``object.__new__`` and the
+attributes its hot-path methods read are set by hand.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(path, name, extra_path):
+    sys.path.insert(0, extra_path)
+    try:
+        for m in ("net", "pinn_solver"):
+            sys.modules.pop(m, None)
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        sys.path.remove(extra_path)
+
+
+def load_reference():
+    # tools.py imports matplotlib (unused); stub it.
+    mpl = types.ModuleType("matplotlib"); mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    sys.modules.setdefault("matplotlib", mpl); sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
+    ns = _load(f"{REF}/NSFnet/pinn_solver.py", "ref_ns_solver", f"{REF}/NSFnet")
+    ev = _load(f"{REF}/ev-NSFnet/pinn_solver.py", "ref_ev_solver", f"{REF}/ev-NSFnet")
+    ns.device = torch.device("cpu")
+    return ns, ev
+
+
+def flat_params(net):
+    return np.concatenate([p.detach().numpy().reshape(-1) for p in net.parameters()]).astype(np.float32)
+
+
+def flat_grads(net):
+    return np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().reshape(-1)
+                           for p in net.parameters()]).astype(np.float32)
+
+
+def boundary(n_side):
+    s = np.linspace(0.0, 1.0, n_side)
+    lid = 1 - np.cosh(10 * (s - 0.5)) / np.cosh(5.0)
+    xb = np.concatenate([s, s, np.zeros(n_side), np.ones(n_side)]).reshape(-1, 1)
+    yb = np.concatenate([np.zeros(n_side), np.ones(n_side), s, s]).reshape(-1, 1)
+    ub = np.concatenate([np.zeros(n_side), lid, np.zeros(n_side), np.zeros(n_side)]).reshape(-1, 1)
+    vb = np.zeros_like(ub)
+    return xb, yb, ub, vb
+
+
+def make_ev(ev, Re, alpha_evm, seed, layers=6, hidden=80, layers_1=4, hidden_1=40, alpha_b=10.0, alpha_e=1.0):
+    torch.manual_seed(seed)
+    P = object.__new__(ev.PysicsInformedNeuralNetwork)
+    P.rank = 0; P.local_rank = 0; P.world_size = 1; P.device = torch.device("cpu"); P.is_distributed = False
+    P.Re = Re; P.vis_t0 = 20.0 / Re; P.alpha_evm = alpha_evm
+    P.alpha_b = alpha_b; P.alpha_e = alpha_e; P.alpha_s = 0.0
+    P.evm = None; P.vis_t = None; P.vis_t_minus = None; P.eq_weights = None
+    P.coord_scale = 1.0; P.coord_scale_sq = 1.0
+    P.x_s = P.y_s = P.u_s = P.v_s = P.p_s = None; P._p_mask = None
+    P.supervision_enabled = False; P.supervision_point_count = 0; P.supervision_total_points = 0
+    P.supervision_has_data = False
+    P.loss_s = 0.0
+    P.N_f = 0; P.current_stage = ' '
+    P.layers = layers; P.hidden_size = hidden; P.layers_1 = layers_1; P.hidden_size_1 = hidden_1
+    P.net = P.initialize_NN(num_ins=2, num_outs=3, num_layers=layers, hidden_size=hidden)
+    P.net_1 = P.initialize_NN(num_ins=2, num_outs=1, num_layers=layers_1, hidden_size=hidden_1)
+    P.opt = torch.optim.Adam(list(P.net.parameters()) + list(P.net_1.parameters()), lr=1e-3, weight_decay=0.0)
+    return P
+
+
+def eq_arrays(P, n):
+    return {f"eq{i+1}": getattr(P, f"eq{i+1}_pred").detach().numpy().reshape(-1).astype(np.float32) for i in range(n)}
+
+
+def case_ns(ns, name, Re, seed, n_f, n_side, scale=1.0):
+    torch.manual_seed(seed)
+    P = ns.PysicsInformedNeuralNetwork(Re=Re, layers=4, hidden_size=120, N_f=n_f, bc_weight=10, eq_weight=1)
+    if scale != 1.0:
+        with torch.no_grad():
+            for p in P.net.parameters():
+                p.mul_(scale)
+    rng = np.random.default_rng(1000 + seed)
+    xf, yf = rng.random((n_f, 1)), rng.random((n_f, 1))
+    P.set_boundary_data(X=boundary(n_side))
+    P.set_eq_training_data(X=(xf, yf))
+    params = flat_params(P.net)
+    loss, (loss_e, loss_b) = P.fwd_computing_loss_2d()
+    P.opt.zero_grad(); loss.backward()
+    u, v, p = P.neural_net_u(P.x_f, P.y_f)
+    d = dict(kind="ns", Re=Re, alpha_b=10.0, alpha_e=1.0, params=params, xf=xf.astype(np.float32), yf=yf.astype(np.float32),
+             n_side=n_side, loss=float(loss), loss_e=float(loss_e), loss_b=float(loss_b),
+             loss_eq=np.array([float(P.loss_eq1), float(P.loss_eq2), float(P.loss_eq3)], np.float32),
+             grad=flat_grads(P.net),
+             uvp=torch.cat([u, v, p], 1).detach().numpy().astype(np.float32), **eq_arrays(P, 3))
+    np.savez_compressed(f"{OUT}/{name}.npz", **d)
+    print(name, "loss", float(loss), "|grad|", np.linalg.norm(d["grad"]))
+
+
+def case_ev(ev, name, Re, seed, n_f, n_side, alpha_evm=0.05, sdf=False, coord_scale=1.0, unfreeze=False,
+            supervised=False, steps=2):
+    P = make_ev(ev, Re, alpha_evm, seed)
+    rng = np.random.default_rng(2000 + seed)
+    xf, yf = rng.random((n_f, 1)), rng.random((n_f, 1))
+    w = None
+    if sdf:
+        d0 = np.minimum(np.minimum(xf, 1 - xf), np.minimum(yf, 1 - yf)).reshape(-1)
+        w = 0.2 + 0.8 * np.exp(-5.0 * d0); w = (w / w.mean()).astype(np.float32)
+    P.set_coordinate_transform(coord_scale if coord_scale != 1.0 else None)
+    P.set_boundary_data(X=boundary(n_side))
+    P.set_eq_training_data(X=(xf, yf), weights=w)      # calls init_vis_t
+    sup = None
+    if supervised:
+        ns_ = 48
+        xs, ys = rng.random((ns_, 1)), rng.random((ns_, 1))
+        us, vs, ps = rng.standard_normal((ns_, 1)) * 0.3, rng.standard_normal((ns_, 1)) * 0.3, rng.standard_normal((ns_, 1)) * 0.1
+        ps[::5] = np.nan
+        P.alpha_s = 2.0
+        P.set_supervised_data((xs, ys, us, vs, ps))
+        sup = np.concatenate([xs, ys, us, vs, ps], 1).astype(np.float32)
+    d = dict(kind="ev", Re=Re, alpha_b=10.0, alpha_e=1.0, alpha_evm=alpha_evm, alpha_s=float(P.alpha_s), coord_scale=coord_scale,
+             xf=xf.astype(np.float32), yf=yf.astype(np.float32), n_side=n_side, unfreeze=int(unfreeze), steps=steps,
+             vis_t_minus_init=np.asarray(P.vis_t_minus, np.float32).reshape(-1))
+    if w is not None:
+        d["w"] = w
+    if sup is not None:
+        d["sup"] = sup
+    if unfreeze:
+        P.defreeze_evm_net(0)
+    else:
+        P.freeze_evm_net(0)
+    for k in range(steps):
+        d[f"params_main_{k}"] = flat_params(P.net)
+        d[f"params_evm_{k}"] = flat_params(P.net_1)
+        loss, (loss_e, loss_b) = P.fwd_computing_loss_2d()
+        P.opt.zero_grad(); loss.backward()
+        d[f"loss_{k}"] = float(loss); d[f"loss_e_{k}"] = float(loss_e); d[f"loss_b_{k}"] = float(loss_b)
+        d[f"loss_s_{k}"] = float(P.loss_s)
+        d[f"loss_eq_{k}"] = np.array([float(P.loss_eq1), float(P.loss_eq2), float(P.loss_eq3), float(P.loss_eq4)], np.float32)
+        d[f"grad_main_{k}"] = flat_grads(P.net)
+        d[f"grad_evm_{k}"] = flat_grads(P.net_1)
+        d[f"vis_t_{k}"] = P.vis_t.detach().numpy().reshape(-1).astype(np.float32) * np.ones(n_f, np.float32)
+        d[f"e_{k}"] = P.evm.detach().numpy().reshape(-1).astype(np.float32)
+        for kk, vv in eq_arrays(P, 4).items():
+            d[f"{kk}_{k}"] = vv
+        P.opt.step()
+        print(name, k, "loss", float(loss), "|g|", np.linalg.norm(d[f"grad_main_{k}"]), "|g_evm|", np.linalg.norm(d[f"grad_evm_{k}"]))
+    np.savez_compressed(f"{OUT}/{name}.npz", **d)
+
+
+def curve_ns(ns, name, Re, seed, n_f, n_side, steps, every):
+    torch.manual_seed(seed)
+    P = ns.PysicsInformedNeuralNetwork(Re=Re, layers=4, hidden_size=120, N_f=n_f, bc_weight=10, eq_weight=1)
+    rng = np.random.default_rng(3000 + seed)
+    xf, yf = rng.random((n_f, 1)), rng.random((n_f, 1))
+    P.set_boundary_data(X=boundary(n_side)); P.set_eq_training_data(X=(xf, yf))
+    params = flat_params(P.net)
+    P.opt.param_groups[0]["lr"] = 1e-3
+    curve = []
+    for k in range(steps):          # body of NSFnet solve_Adam (NSFnet/pinn_solver.py:250-254)
+        loss, _ = P.fwd_computing_loss_2d()
+        loss.backward(); P.opt.step(); P.opt.zero_grad()
+        if k % every == 0:
+            curve.append(float(loss))
+    np.savez_compressed(f"{OUT}/{name}.npz", kind="ns_curve", Re=Re, alpha_b=10.0, alpha_e=1.0, params=params,
+                        xf=xf.astype(np.float32), yf=yf.astype(np.float32), n_side=n_side, steps=steps, every=every,
+                        lr=1e-3, curve=np.array(curve, np.float64))
+    print(name, curve[:3], curve[-3:])
+
+
+def curve_ev(ev, name, Re, seed, n_f, n_side, steps, every, alpha_evm=0.05):
+    P = make_ev(ev, Re, alpha_evm, seed)
+    rng = np.random.default_rng(4000 + seed)
+    xf, yf = rng.random((n_f, 1)), rng.random((n_f, 1))
+    P.set_boundary_data(X=boundary(n_side)); P.set_eq_training_data(X=(xf, yf))
+    pm, pe = flat_params(P.net), flat_params(P.net_1)
+    P.log_interval = 10 ** 9
+    P.print_log = lambda *a, **k: None
+    P.save = lambda *a, **k: None
+    curve = []
+    orig = P.fwd_computing_loss_2d
+
+    def rec():
+        out = orig()
+        curve.append(float(out[0]))
+        return out
+    P.opt.param_groups[0]["lr"] = 1e-3
+    P.solve_Adam(rec, steps)        # the reference's own loop incl. freeze bookkeeping (ev :440-487)
+    np.savez_compressed(f"{OUT}/{name}.npz", kind="ev_curve", Re=Re, alpha_b=10.0, alpha_e=1.0, alpha_evm=alpha_evm,
+                        params_main=pm, params_evm=pe, xf=xf.astype(np.float32), yf=yf.astype(np.float32), n_side=n_side,
+                        steps=steps, every=every, lr=1e-3, curve=np.array(curve[::every], np.float64))
+    print(name, curve[:3], curve[-3:])
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    ns, ev = load_reference()
+    case_ns(ns, "ns_re100_init", 100, 0, 192, 17)
+    case_ns(ns, "ns_re1000_x2p5", 1000, 1, 192, 17, scale=2.5)
+    case_ev(ev, "ev_re2000_lag", 2000, 0, 192, 17, steps=3)
+    case_ev(ev, "ev_re5000_sdf_unfrozen", 5000, 1, 160, 9, alpha_evm=0.03, sdf=True, unfreeze=True, steps=2)
+    case_ev(ev, "ev_re3000_scale_sup", 3000, 2, 128, 9, coord_scale=2.0, supervised=True, steps=1)
+    curve_ns(ns, "curve_ns_re100", 100, 0, 512, 33, 200, 10)
+    curve_ns(ns, "curve_ns_re1000", 1000, 0, 512, 33, 200, 10)
+    curve_ev(ev, "curve_ev_re2000", 2000, 0, 512, 33, 100, 5)
