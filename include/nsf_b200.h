@@ -1,0 +1,166 @@
+/*
+ * nsf_b200.h -- C ABI of the B200-native NSFnet / ev-NSFnet training hot path.
+ *
+ * The reference (latteine1217/NSFnet) has no FFI: its seam is the Python method API of
+ * `PysicsInformedNeuralNetwork` (ev-NSFnet/pinn_solver.py, NSFnet/pinn_solver.py).  This header
+ * is the boundary a binding for that seam loads (ctypes / cffi / cgo / JNI all work: plain
+ * pointers and sizes, no C++ or torch types).  Each entry point names the reference code it
+ * replaces.
+ *
+ * Conventions
+ *   - every function returns an int status (NSF_OK == 0, negative == error) and never throws;
+ *     nsf_last_error() returns a thread-local message for the last failure on this thread;
+ *   - every buffer is a caller-owned CUDA *device* pointer, fp32, contiguous, 16-byte aligned
+ *     (what `tensor.data_ptr()` gives for a fresh torch CUDA tensor); nothing is retained after
+ *     the call returns except inside the opaque context;
+ *   - all work is enqueued asynchronously on the caller-supplied `cudaStream_t` (passed as
+ *     void*; NULL = legacy default stream); results are ready when the stream reaches that point;
+ *   - flat parameter / gradient order is FCNet's state_dict order (net.py:38-46):
+ *     W0 [out,in] row-major, b0, W1, b1, ...;
+ *   - a context is used by one host thread at a time; contexts on different devices are
+ *     independent (one process per GPU under torchrun, as ev-NSFnet/train.py:22-43);
+ *   - there is NO CPU fallback: nsf_create fails with NSF_E_ARCH unless the device is sm_100.
+ */
+#ifndef NSF_B200_H
+#define NSF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSF_ABI_VERSION 1
+
+enum {
+  NSF_OK = 0,
+  NSF_E_ARG = -1,    /* null / misaligned pointer, bad size or flag                    */
+  NSF_E_ARCH = -2,   /* device is not compute capability 10.x                          */
+  NSF_E_CUDA = -3,   /* a CUDA runtime call failed (message in nsf_last_error)         */
+  NSF_E_SHAPE = -4,  /* network shape outside what the kernels cover                   */
+  NSF_E_ALLOC = -5   /* workspace allocation failed                                    */
+};
+
+/* FCNet(num_ins, num_outs, num_layers, hidden_size) -- net.py:23-30. */
+typedef struct {
+  int32_t n_in;            /* must be 2 (x, y)                       */
+  int32_t n_out;           /* 3 for the u,v,p net, 1 for the EVM net */
+  int32_t n_hidden_layers; /* num_layers  (tanh layers), 1..16       */
+  int32_t hidden;          /* hidden_size, 4..128                    */
+} NsfNetDesc;
+
+/* flags of NsfPhysics */
+#define NSF_HAS_EVM 1u       /* ev-NSFnet: second net, eq4, lagged entropy viscosity            */
+#define NSF_EVM_TRAINABLE 2u /* net_1 unfrozen (ev :501-511): also produce its gradient         */
+
+/* Scalars of one loss evaluation -- ev-NSFnet/pinn_solver.py:32-54,67,311-342,387-397,426. */
+typedef struct {
+  float inv_Re;      /* 1/Re                                                         */
+  float vis_t0;      /* 20/Re, cap of the entropy viscosity (ev :67)                 */
+  float alpha_evm;   /* alpha in vis_t_minus = alpha*|e| (ev :334)                   */
+  float alpha_e;     /* eq_weight (ev :426)                                          */
+  float coord_scale; /* 1.0 unless coordinate_transform (ev :311-324)                */
+  float eq4_weight;  /* 0.1 (ev :397)                                                */
+  uint32_t flags;    /* NSF_HAS_EVM | NSF_EVM_TRAINABLE                              */
+  uint32_t reserved;
+  double n_f_norm;   /* denominator of the residual means; <=0 means n_f. Under data parallelism
+                        pass the GLOBAL point count so that summing gradients over ranks gives
+                        the gradient on the union of the shards. */
+} NsfPhysics;
+
+/* A "value-stream MSE against targets" block: the boundary term (ev :374-379) and the optional
+ * supervised term (ev :399-411) are both instances.  loss contribution =
+ *   cu*sum (u-u_hat)^2 + cv*sum (v-v_hat)^2 + cp*sum_{isfinite(p)} (p-p_hat)^2
+ * so boundary = {cu = cv = alpha_b/N_b, cp = 0}. */
+typedef struct {
+  const float* x;
+  const float* y;
+  const float* u;  /* targets */
+  const float* v;
+  const float* p;  /* may be NULL; NaN entries are masked out (ev :404-409) */
+  int64_t n;
+  float cu, cv, cp;
+  int32_t reserved;
+} NsfDataBlock;
+
+#define NSF_MAX_BLOCKS 2
+
+/* loss_parts layout (device float[NSF_LOSS_SLOTS], UNNORMALISED sums so that they all-reduce):
+ *   [0..3]  sum w*eq_k^2, k=1..4           [4] sum vis_t        [5] number of collocation points
+ *   [6+4b+0..3]  block b: sum du^2, sum dv^2, sum_masked dp^2, number of finite p targets */
+#define NSF_LOSS_SLOTS 16
+
+typedef struct NsfCtx NsfCtx;
+
+/* Library / build info. */
+int nsf_abi_version(void);
+const char* nsf_last_error(void);
+
+/* Create / destroy the per-device context (workspace: activation stash, per-CTA gradient
+ * partials, packed weight images).  evm may be NULL (plain NSFnet).  Replaces nothing in the
+ * reference; it is the analogue of building the nets on `cuda:local_rank` (ev :61-63,97-100). */
+int nsf_create(int device, const NsfNetDesc* main_net, const NsfNetDesc* evm_or_null, NsfCtx** out);
+int nsf_destroy(NsfCtx* ctx);
+
+/* Select the kernel family of the hidden-layer contractions: 0 = auto (tcgen05 when the shape is
+ * covered, else FFMA), 1 = force the FP32 FFMA kernels, 2 = force tcgen05 3xTF32 (NSF_E_SHAPE if
+ * the shape is not covered). */
+int nsf_set_path(NsfCtx* ctx, int path);
+/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 2 tcgen05),
+ * [2]=kernel launches issued by the last nsf_* call, [3]=workspace bytes. */
+int nsf_get_info(NsfCtx* ctx, int64_t info[4]);
+
+/* One `fwd_computing_loss_2d()` + `loss.backward()`:
+ *   ev-NSFnet/pinn_solver.py:372-428 + :468-469 (DDP all-reduce excluded), i.e.
+ *   neural_net_u on the blocks (:280-288), neural_net_equations on the collocation points
+ *   (:290-342, replacing the 7 autograd sweeps :301-309), the weighted MSE (:387-397) and the
+ *   parameter gradient.  NSFnet/pinn_solver.py:197-226 + :252 is the same call without NSF_HAS_EVM.
+ *
+ *   params_main/params_evm : flat parameters (state_dict order)
+ *   x,y [n_f]              : collocation points;  w [n_f] or NULL: SDF weights (ev :387-392)
+ *   vis_t_minus_in [n_f]   : alpha*|e| of the previous evaluation, or NULL -> constant vis_t0
+ *                            (ev :327-331);  vis_t_minus_out [n_f] (may alias _in): this step's
+ *                            alpha_evm*|e| (ev :334).  Both ignored without NSF_HAS_EVM.
+ *   blocks[n_blocks]       : boundary / supervised MSE terms (host array of device pointers)
+ *   grad_main, grad_evm    : OVERWRITTEN with d(loss)/d(params); grad_evm untouched unless
+ *                            NSF_EVM_TRAINABLE
+ *   loss_parts             : device float[NSF_LOSS_SLOTS], overwritten
+ *   residuals_out          : NULL or device float[4*n_f] = eq1|eq2|eq3|eq4 (eq4 = 0 without EVM)
+ *   e_out, vis_t_out       : NULL or device float[n_f] (self.evm, self.vis_t)
+ */
+int nsf_step(NsfCtx* ctx, const float* params_main, const float* params_evm,
+             const float* x, const float* y, const float* w,
+             const float* vis_t_minus_in, float* vis_t_minus_out, int64_t n_f,
+             const NsfDataBlock* blocks, int32_t n_blocks, const NsfPhysics* phys,
+             float* grad_main, float* grad_evm, float* loss_parts,
+             float* residuals_out, float* e_out, float* vis_t_out, void* stream);
+
+/* `neural_net_equations(x, y)` without gradient (ev :290-342; used by `divergence` :761-765):
+ * forward jet only.  residuals_out = eq1|eq2|eq3|eq4 [4*n].  Updates the lag state exactly as
+ * the reference does when vis_t_minus_out != NULL. */
+int nsf_residuals(NsfCtx* ctx, const float* params_main, const float* params_evm,
+                  const float* x, const float* y, const float* vis_t_minus_in,
+                  float* vis_t_minus_out, int64_t n, const NsfPhysics* phys,
+                  float* residuals_out, float* e_out, float* vis_t_out, void* stream);
+
+/* `neural_net_u(x, y)` (ev :280-288; evaluate/test :669-740): value-only forward of one net.
+ * which = 0 main net (out [n,3] row-major u,v,p), 1 EVM net (out [n,1]). */
+int nsf_forward(NsfCtx* ctx, int32_t which, const float* params, const float* x, const float* y,
+                int64_t n, float* out, void* stream);
+
+/* Fused Adam on a flat buffer (torch.optim.Adam semantics, betas/eps/wd=0 as ev :126-129):
+ * step is the 1-based step count after increment.  "Next" row f.1 of the scope table. */
+int nsf_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+             float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+             void* stream);
+
+/* Debug / validation: runs one tcgen05 TF32 GEMM D[128,n] = A[128,k] * B[n,k]^T with the same
+ * shared-memory descriptors the jet kernel uses (variant selects operand majors / 3xTF32 split)
+ * so tests can check the descriptor encodings against a CPU product. */
+int nsf_selftest_umma(int device, int32_t variant, const float* a, const float* b, float* d,
+                      int32_t n, int32_t k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSF_B200_H */

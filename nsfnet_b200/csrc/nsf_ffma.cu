@@ -1,0 +1,185 @@
+// FP32 FFMA kernels of libnsf_b200.so: the jet step / residual / value kernels (nsf_ffma_body.h),
+// the parameter packer, the gradient-row reduction and a fused Adam.
+#include "nsf_internal.h"
+#include "nsf_ffma_body.h"
+
+#include <vector>
+
+int nsf_ffma_pt(int ns, int hp) { return (ns == 4 && hp > 80) ? 16 : 32; }
+
+#ifndef NSF_EMU
+// ---------------------------------------------------------------------------------------------
+// CUDA
+// ---------------------------------------------------------------------------------------------
+template <int NS, int PT>
+__global__ void __launch_bounds__(256) nsf_ffma_kernel(const NsfKernelArgs a) {
+  extern __shared__ __align__(16) float nsf_smem[];
+  nsf_cta_program<NS, PT>(a, nsf_smem, (int)blockIdx.x, (int)gridDim.x, (int)blockDim.x);
+}
+
+template <int NS, int PT>
+static int launch_t(const NsfKernelArgs& a, int grid, int nt, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    NSF_CUDA_OK(cudaFuncSetAttribute(nsf_ffma_kernel<NS, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  nsf_ffma_kernel<NS, PT><<<grid, nt, smem, st>>>(a);
+  NSF_CUDA_OK(cudaGetLastError());
+  return NSF_OK;
+}
+
+template <int NS, int PT>
+static int occ_t(int nt, size_t smem) {
+  int nb = 0;
+  if (cudaFuncSetAttribute(nsf_ffma_kernel<NS, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nsf_ffma_kernel<NS, PT>, nt, smem) != cudaSuccess) return 0;
+  return nb;
+}
+
+int nsf_ffma_occupancy(int ns, int hp) {
+  const int pt = nsf_ffma_pt(ns, hp);
+  const int nt = (hp / 4) * (pt / 4);
+  const size_t smem = (size_t)nsf_ffma_smem_floats(ns, pt, hp) * sizeof(float);
+  if (ns == 4) return pt == 32 ? occ_t<4, 32>(nt, smem) : occ_t<4, 16>(nt, smem);
+  return occ_t<1, 32>(nt, smem);
+}
+
+int nsf_ffma_launch(NsfKernelArgs& a, int ns, int grid, nsf_stream_t st) {
+  const int hp = a.g.HP;
+  const int pt = nsf_ffma_pt(ns, hp);
+  const int nt = (hp / 4) * (pt / 4);
+  const size_t smem = (size_t)nsf_ffma_smem_floats(ns, pt, hp) * sizeof(float);
+  a.n_tiles = (int)((a.n + pt - 1) / pt);
+  if (a.n_tiles <= 0 || grid <= 0) return NSF_OK;
+  if (ns == 4) return pt == 32 ? launch_t<4, 32>(a, grid, nt, smem, st) : launch_t<4, 16>(a, grid, nt, smem, st);
+  return launch_t<1, 32>(a, grid, nt, smem, st);
+}
+
+__global__ void nsf_pack_kernel(NsfNetGeom g, const float* __restrict__ flat, float* __restrict__ pk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.pk_size()) pk[i] = nsf_pack_value(g, flat, i);
+}
+
+int nsf_pack_launch(const NsfNetGeom& g, const float* flat, float* pk, nsf_stream_t st) {
+  const int n = g.pk_size();
+  nsf_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, flat, pk);
+  NSF_CUDA_OK(cudaGetLastError());
+  return NSF_OK;
+}
+
+// grad[i] = sum over rows of scratch[row][map[i]] (fp64 accumulation, fixed order => bitwise
+// reproducible); loss_parts[s] likewise.
+__global__ void nsf_finalize_kernel(NsfNetGeom g, const float* __restrict__ scratch, int rows, const int* __restrict__ map,
+                                    float* __restrict__ grad, float* __restrict__ loss_parts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = g.n_params;
+  if (i >= np + NSF_LOSS_SLOTS) return;
+  const bool is_loss = i >= np;
+  if (is_loss ? (loss_parts == nullptr) : (grad == nullptr)) return;
+  const int col = is_loss ? g.gs_loss() + (i - np) : map[i];
+  const long long stride = g.gs_row();
+  double acc = 0.0;
+  for (int r = 0; r < rows; ++r) acc += (double)scratch[r * stride + col];
+  if (is_loss) loss_parts[i - np] = (float)acc;
+  else grad[i] = (float)acc;
+}
+
+int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, const int* map, float* grad,
+                        float* loss_parts, nsf_stream_t st) {
+  const int n = g.n_params + NSF_LOSS_SLOTS;
+  nsf_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(g, scratch, rows, map, grad, loss_parts);
+  NSF_CUDA_OK(cudaGetLastError());
+  return NSF_OK;
+}
+
+// torch.optim.Adam (no amsgrad, wd = 0): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void nsf_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float gs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gs;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+int nsf_adam_launch(float* params, const float* grad, float* m, float* v, long long n, float lr, float b1, float b2,
+                    float eps, float bc1, float bc2, float grad_scale, nsf_stream_t st) {
+  if (n <= 0) return NSF_OK;
+  nsf_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  NSF_CUDA_OK(cudaGetLastError());
+  return NSF_OK;
+}
+
+#else
+// ---------------------------------------------------------------------------------------------
+// host SIMT emulation (tests/emu only)
+// ---------------------------------------------------------------------------------------------
+#include <cmath>
+
+int nsf_emu_reverse = 0;
+extern "C" void nsf_emu_set_reverse(int v) { nsf_emu_reverse = v; }
+
+template <int NS, int PT>
+static void emu_run(const NsfKernelArgs& a, int grid, int nt, size_t smem_floats) {
+  std::vector<float> smem(smem_floats);
+  std::vector<NsfRegs<NS>> regs(nt);
+  for (int bid = 0; bid < grid; ++bid) {
+    std::fill(smem.begin(), smem.end(), NAN);  // catch reads of unwritten shared memory
+    nsf_cta_program<NS, PT>(a, smem.data(), bid, grid, nt, regs.data());
+  }
+}
+
+int nsf_ffma_occupancy(int ns, int hp) { return ns == 4 ? (nsf_ffma_pt(ns, hp) == 32 ? 2 : 3) : 4; }
+
+int nsf_ffma_launch(NsfKernelArgs& a, int ns, int grid, nsf_stream_t) {
+  const int hp = a.g.HP;
+  const int pt = nsf_ffma_pt(ns, hp);
+  const int nt = (hp / 4) * (pt / 4);
+  const size_t sf = (size_t)nsf_ffma_smem_floats(ns, pt, hp);
+  a.n_tiles = (int)((a.n + pt - 1) / pt);
+  if (a.n_tiles <= 0 || grid <= 0) return NSF_OK;
+  if (ns == 4) { if (pt == 32) emu_run<4, 32>(a, grid, nt, sf); else emu_run<4, 16>(a, grid, nt, sf); }
+  else emu_run<1, 32>(a, grid, nt, sf);
+  return NSF_OK;
+}
+
+int nsf_pack_launch(const NsfNetGeom& g, const float* flat, float* pk, nsf_stream_t) {
+  for (int i = 0; i < g.pk_size(); ++i) pk[i] = nsf_pack_value(g, flat, i);
+  return NSF_OK;
+}
+
+int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, const int* map, float* grad,
+                        float* loss_parts, nsf_stream_t) {
+  const long long stride = g.gs_row();
+  if (grad)
+    for (int i = 0; i < g.n_params; ++i) {
+      double acc = 0;
+      for (int r = 0; r < rows; ++r) acc += (double)scratch[r * stride + map[i]];
+      grad[i] = (float)acc;
+    }
+  if (loss_parts)
+    for (int s = 0; s < NSF_LOSS_SLOTS; ++s) {
+      double acc = 0;
+      for (int r = 0; r < rows; ++r) acc += (double)scratch[r * stride + g.gs_loss() + s];
+      loss_parts[s] = (float)acc;
+    }
+  return NSF_OK;
+}
+
+int nsf_adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                    float eps, float bc1, float bc2, float gs, nsf_stream_t) {
+  for (long long i = 0; i < n; ++i) {
+    const float gi = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * (mi / (std::sqrt(vi) / std::sqrt(bc2) + eps));
+  }
+  return NSF_OK;
+}
+#endif

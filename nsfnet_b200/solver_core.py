@@ -1,0 +1,468 @@
+"""Shared implementation of the two ``PysicsInformedNeuralNetwork`` solvers (NSFnet / ev-NSFnet).
+
+Mirrors the reference's solver API (NSFnet/pinn_solver.py:26-389, ev-NSFnet/pinn_solver.py:27-765):
+same constructor keywords, setters, ``neural_net_u``, ``neural_net_equations``,
+``fwd_computing_loss_2d`` -> ``(loss, [loss_e, loss_b])``, ``train`` / ``solve_Adam``,
+``freeze_evm_net`` / ``defreeze_evm_net``, ``evaluate`` / ``test`` / ``save``.  Underneath, one
+loss + gradient evaluation is ONE call into libnsf_b200.so (``nsf_step``, include/nsf_b200.h)
+instead of two module forwards, seven ``torch.autograd.grad`` sweeps and a backward pass; the
+returned ``loss`` is a tensor whose ``.backward()`` fills ``p.grad`` for every parameter with
+``requires_grad`` (so the reference's own loops, or an L-BFGS closure, work unchanged).  Adam
+stays ``torch.optim.Adam``.
+
+Data parallelism (ev-NSFnet/pinn_solver.py:103-106,142-184,414-424): points are sharded in
+contiguous blocks exactly like the reference; instead of DDP buckets + three scalar all-reduces
+there is a single ``all_reduce(SUM)`` of ``[grad_main | grad_evm | loss partial sums]`` and the
+means are taken over the GLOBAL point counts, so the W-rank gradient equals the 1-rank gradient
+on the union of the shards.  ``ddp_compat=True`` reproduces the reference's extra 1/W factor.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from .net import FCNet
+
+
+def _dev_f32(a, device) -> torch.Tensor:
+    """numpy / tensor -> contiguous 1-D fp32 device tensor (the reference's .float().to(device))."""
+    if isinstance(a, torch.Tensor):
+        t = a.detach()
+    else:
+        t = torch.as_tensor(np.asarray(a))
+    return t.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+
+
+class _StepFn(torch.autograd.Function):
+    """loss = nsf_step(...); backward hands out the gradient the kernel already produced."""
+
+    @staticmethod
+    def forward(ctx, solver, *params):
+        loss = solver._launch_step()
+        ctx.solver = solver
+        ctx.n_in = len(params)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        s = ctx.solver
+        scaled = s._gbuf * gout
+        outs = []
+        for (net_id, off, numel, shape, req) in s._param_slices:
+            if req:
+                base = 0 if net_id == 0 else s._n_main
+                outs.append(scaled[base + off: base + off + numel].view(shape))
+        assert len(outs) == ctx.n_in
+        return (None, *outs)
+
+
+class SolverBase:
+    tb_writer = None
+    global_step = 0
+    HAS_EVM = False
+
+    # ------------------------------------------------------------------------------------
+    def _init_common(self, Re, layers, hidden_size, N_f, bc_weight, eq_weight, num_ins, num_outs, learning_rate,
+                     net_params, opt, layers_1=None, hidden_size_1=None, num_outs_1=1, net_params_1=None,
+                     alpha_evm=0.0, supervised_data_weight=0.0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("nsfnet_b200 needs a CUDA device (sm_100); there is no CPU path")
+        self.rank = int(os.environ.get("RANK", 0))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        self.world_size = int(os.environ.get("WORLD_SIZE", 1))
+        self.device = torch.device(f"cuda:{self.local_rank}")
+        torch.cuda.set_device(self.local_rank)
+        self._lib = _capi.load()
+
+        self.evm = None
+        self.Re = Re
+        self.layers, self.hidden_size, self.N_f = layers, hidden_size, N_f
+        self.layers_1, self.hidden_size_1 = layers_1, hidden_size_1
+        self.current_stage = " "
+        self.alpha_evm = alpha_evm
+        self.alpha_b, self.alpha_e, self.alpha_s = bc_weight, eq_weight, supervised_data_weight
+        self.loss_b = self.loss_e = self.loss_s = 0.0
+        self.x_s = self.y_s = self.u_s = self.v_s = self.p_s = None
+        self.supervision_point_count = 0
+        self.supervision_total_points = 0
+        self.supervision_has_data = False
+        self.supervision_enabled = False
+        self._n_s_global = 0
+        self._n_ps_global = 0
+        self.eq_weights = None
+        self.coord_scale = 1.0
+        self.coord_scale_sq = 1.0
+        self.vis_t = None
+        self.vis_t_minus = None
+        self.ddp_compat = False
+        self.store_residuals = True
+        self.x_b = self.x_f = None
+
+        self.net = self.initialize_NN(num_ins=num_ins, num_outs=num_outs, num_layers=layers, hidden_size=hidden_size).to(self.device)
+        self.net_1 = None
+        if self.HAS_EVM:
+            self.net_1 = self.initialize_NN(num_ins=num_ins, num_outs=num_outs_1, num_layers=layers_1,
+                                            hidden_size=hidden_size_1).to(self.device)
+        self.is_distributed = dist.is_available() and dist.is_initialized() and self.world_size > 1
+        if net_params:
+            if self.rank == 0:
+                print(f"Loading net params from {net_params}")
+            self.net.load_state_dict(torch.load(net_params, map_location=self.device))
+        if net_params_1 and self.HAS_EVM:
+            if self.rank == 0:
+                print(f"Loading net_1 params from {net_params_1}")
+            self.net_1.load_state_dict(torch.load(net_params_1, map_location=self.device))
+        self.net.flatten_()
+        if self.net_1 is not None:
+            self.net_1.flatten_()
+        if self.is_distributed:  # what DDP's constructor does (ev :103-106): rank 0's weights everywhere
+            dist.broadcast(self.net.flat_params(), src=0)
+            if self.net_1 is not None:
+                dist.broadcast(self.net_1.flat_params(), src=0)
+
+        self._ctx = _capi.Context(self._lib, self.local_rank, self.net.desc, self.net_1.desc if self.net_1 is not None else None)
+        self._n_main = self.net.flat_params().numel()
+        self._n_evm = self.net_1.flat_params().numel() if self.net_1 is not None else 0
+        # [grad_main | grad_evm | loss_parts]: one buffer => one all-reduce
+        self._buf = torch.zeros(self._n_main + self._n_evm + _capi.NSF_LOSS_SLOTS, dtype=torch.float32, device=self.device)
+        self._gbuf = self._buf[: self._n_main + self._n_evm]
+        self._parts = self._buf[self._n_main + self._n_evm:]
+        self._param_slices = []
+
+        params = list(self.net.parameters()) + (list(self.net_1.parameters()) if self.net_1 is not None else [])
+        self.opt = torch.optim.Adam(params, lr=learning_rate, weight_decay=0.0) if not opt else opt
+
+    def initialize_NN(self, num_ins=3, num_outs=3, num_layers=10, hidden_size=50):
+        return FCNet(num_ins=num_ins, num_outs=num_outs, num_layers=num_layers, hidden_size=hidden_size,
+                     activation=torch.nn.Tanh)
+
+    # ---- setters (ev :142-262, NSFnet :82-110) -------------------------------------------------
+    def _shard(self, total):
+        per = total // self.world_size
+        s = self.rank * per
+        e = s + per if self.rank < self.world_size - 1 else total
+        return s, e
+
+    def set_boundary_data(self, X=None, time=False):
+        total = np.asarray(X[0]).shape[0]
+        s, e = self._shard(total)
+        self.x_b, self.y_b, self.u_b, self.v_b = [_dev_f32(np.asarray(a)[s:e], self.device) for a in X[:4]]
+        self._n_b_global = total
+        if self.rank == 0:
+            print(f"GPU {self.rank}: Processing {e - s} boundary points out of {total} total")
+
+    def set_eq_training_data(self, X=None, time=False, weights=None):
+        total = np.asarray(X[0]).shape[0] if not isinstance(X[0], torch.Tensor) else X[0].shape[0]
+        s, e = self._shard(total)
+        if isinstance(X[0], torch.Tensor):
+            self.x_f = _dev_f32(X[0].reshape(-1)[s:e], self.device)
+            self.y_f = _dev_f32(X[1].reshape(-1)[s:e], self.device)
+        else:
+            self.x_f = _dev_f32(np.asarray(X[0])[s:e], self.device)
+            self.y_f = _dev_f32(np.asarray(X[1])[s:e], self.device)
+        if weights is not None:
+            w = weights if isinstance(weights, torch.Tensor) else np.asarray(weights)
+            self.eq_weights = _dev_f32(w.reshape(-1)[s:e], self.device)
+        else:
+            self.eq_weights = None
+        self._n_f_global = total
+        n = self.x_f.numel()
+        self._resid = torch.empty(4 * n, dtype=torch.float32, device=self.device)
+        self._e = torch.empty(n, dtype=torch.float32, device=self.device)
+        self._vis = torch.empty(n, dtype=torch.float32, device=self.device)
+        if self.rank == 0:
+            print(f"GPU {self.rank}: Processing {e - s} equation points out of {total} total")
+        if self.HAS_EVM:
+            self.init_vis_t()
+
+    def set_coordinate_transform(self, scale):
+        if scale is None or scale <= 0:
+            self.coord_scale, self.coord_scale_sq = 1.0, 1.0
+        else:
+            self.coord_scale = float(scale)
+            self.coord_scale_sq = self.coord_scale ** 2
+
+    def clear_supervised_data(self):
+        self.x_s = self.y_s = self.u_s = self.v_s = self.p_s = None
+        self.supervision_point_count = 0
+        self.supervision_total_points = 0
+        self.supervision_has_data = False
+        self.supervision_enabled = False
+        self._n_s_global = self._n_ps_global = 0
+
+    def set_supervised_data(self, data):
+        if data is None:
+            return self.clear_supervised_data()
+        x, y, u, v, p = [None if a is None else np.asarray(a).reshape(-1) for a in data]
+        total = x.shape[0]
+        self.supervision_total_points = int(total)
+        if total == 0:
+            return self.clear_supervised_data()
+        idx = np.array_split(np.arange(total), self.world_size)[self.rank] if self.world_size > 1 else slice(None)
+        self.x_s, self.y_s, self.u_s, self.v_s = [_dev_f32(a[idx], self.device) for a in (x, y, u, v)]
+        self.p_s = _dev_f32(p[idx], self.device) if p is not None else None
+        self.supervision_point_count = int(self.x_s.numel())
+        self._n_s_global = total
+        self._n_ps_global = int(np.isfinite(p).sum()) if p is not None else 0
+        self.supervision_has_data = True
+        self.supervision_enabled = self.alpha_s != 0.0
+
+    def set_supervised_loss_weight(self, weight):
+        self.alpha_s = float(weight)
+        self.supervision_enabled = self.supervision_has_data and self.alpha_s != 0.0
+
+    def set_optimizers(self, opt):
+        self.opt = opt
+
+    def set_stage(self, stage):
+        self.stage = stage
+        self.current_stage = stage
+
+    def set_alpha_evm(self, alpha):
+        self.alpha_evm = alpha
+
+    def set_eq_training_func(self, train_data_func):
+        self.train_data_func = train_data_func
+
+    # ---- native calls ---------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _phys(self, n_f_norm=0.0):
+        trainable = self.HAS_EVM and any(p.requires_grad for p in self.net_1.parameters())
+        return _capi.physics(float(self.Re), vis_t0=(20.0 / self.Re) if self.HAS_EVM else 0.0, alpha_evm=float(self.alpha_evm),
+                             alpha_e=float(self.alpha_e), coord_scale=float(self.coord_scale), eq4_weight=0.1,
+                             has_evm=self.HAS_EVM, evm_trainable=trainable, n_f_norm=float(n_f_norm))
+
+    def _forward_net(self, which, x, y):
+        net = self.net if which == 0 else self.net_1
+        x = _dev_f32(x, self.device); y = _dev_f32(y, self.device)
+        n = x.numel()
+        out = torch.empty((n, net.num_outs), dtype=torch.float32, device=self.device)
+        self._ctx.forward(which, net.flat_params().data_ptr(), x.data_ptr(), y.data_ptr(), n, out.data_ptr(), self._stream())
+        return out
+
+    def init_vis_t(self):
+        """vis_t_minus = alpha_evm * |e(x_f, y_f)| with the current weights (ev :138-140)."""
+        e = self._forward_net(1, self.x_f, self.y_f)
+        self.vis_t_minus = (float(self.alpha_evm) * e.abs()).reshape(-1).contiguous()
+
+    def _launch_step(self):
+        net, net1 = self.net, self.net_1
+        pm = net.flat_params()
+        pe = net1.flat_params() if net1 is not None else None
+        n_f = self.x_f.numel()
+        W = self.world_size if self.is_distributed else 1
+        n_f_glob = self._n_f_global if W > 1 else n_f
+        n_b = self.x_b.numel() if self.x_b is not None else 0
+        n_b_glob = self._n_b_global if W > 1 else n_b
+        blocks = []
+        if n_b > 0:
+            c = float(self.alpha_b) / float(n_b_glob)
+            blocks.append(_capi.NsfDataBlock(self.x_b.data_ptr(), self.y_b.data_ptr(), self.u_b.data_ptr(), self.v_b.data_ptr(),
+                                             None, n_b, c, c, 0.0, 0))
+        sup = self.supervision_enabled and self.x_s is not None and self.supervision_point_count > 0
+        if sup:
+            n_s_glob = self._n_s_global if W > 1 else self.supervision_point_count
+            cs = float(self.alpha_s) / float(n_s_glob)
+            cp = float(self.alpha_s) / float(self._n_ps_global) if (self.p_s is not None and self._n_ps_global > 0) else 0.0
+            blocks.append(_capi.NsfDataBlock(self.x_s.data_ptr(), self.y_s.data_ptr(), self.u_s.data_ptr(), self.v_s.data_ptr(),
+                                             self.p_s.data_ptr() if self.p_s is not None else None,
+                                             self.supervision_point_count, cs, cs, cp, 0))
+        w = self.eq_weights if (self.eq_weights is not None and self.eq_weights.numel() == n_f) else None
+        vtm = self.vis_t_minus if (self.HAS_EVM and self.vis_t_minus is not None and self.vis_t_minus.numel() == n_f) else None
+        if self.HAS_EVM and vtm is None:
+            self.vis_t_minus = torch.empty(n_f, dtype=torch.float32, device=self.device)
+        phys = self._phys(n_f_glob)
+        gm = self._buf
+        ge = self._buf[self._n_main:] if self._n_evm else None
+        keep = self.store_residuals
+        self._ctx.step(pm.data_ptr(), pe.data_ptr() if pe is not None else None, self.x_f.data_ptr(), self.y_f.data_ptr(),
+                       w.data_ptr() if w is not None else None, vtm.data_ptr() if vtm is not None else None,
+                       self.vis_t_minus.data_ptr() if self.HAS_EVM else None, n_f, blocks, phys,
+                       gm.data_ptr(), ge.data_ptr() if ge is not None else None, self._parts.data_ptr(),
+                       self._resid.data_ptr() if keep else None, self._e.data_ptr() if self.HAS_EVM else None,
+                       self._vis.data_ptr() if self.HAS_EVM else None, self._stream())
+        if self.HAS_EVM and not (phys.flags & _capi.NSF_EVM_TRAINABLE):
+            self._buf[self._n_main:self._n_main + self._n_evm].zero_()
+        if W > 1:
+            dist.all_reduce(self._buf, op=dist.ReduceOp.SUM)
+            if self.ddp_compat:  # the reference's tracked `loss /= world_size` on top of DDP averaging
+                self._gbuf.div_(W)
+
+        P = self._parts
+        nf = float(n_f_glob)
+        self.loss_eq1, self.loss_eq2, self.loss_eq3 = P[0] / nf, P[1] / nf, P[2] / nf
+        loss_e = self.loss_eq1 + self.loss_eq2 + self.loss_eq3
+        if self.HAS_EVM:
+            self.loss_eq4 = P[3] / nf
+            loss_e = loss_e + 0.1 * self.loss_eq4
+        self.loss_e = loss_e
+        self.loss_b = (P[6] + P[7]) / float(max(n_b_glob, 1))
+        loss = self.alpha_b * self.loss_b + self.alpha_e * self.loss_e
+        if sup:
+            k = 10 if n_b > 0 else 6
+            n_s_glob = self._n_s_global if W > 1 else self.supervision_point_count
+            self.loss_s = (P[k] + P[k + 1]) / float(n_s_glob) + (P[k + 2] / float(self._n_ps_global) if self._n_ps_global > 0 else 0.0)
+            loss = loss + self.alpha_s * self.loss_s
+        else:
+            self.loss_s = torch.zeros((), device=self.device)
+        n = n_f
+        if keep:
+            self.eq1_pred, self.eq2_pred, self.eq3_pred = [self._resid[k * n:(k + 1) * n].view(n, 1) for k in range(3)]
+            if self.HAS_EVM:
+                self.eq4_pred = self._resid[3 * n:4 * n].view(n, 1)
+        if self.HAS_EVM:
+            self.evm = self._e.view(n, 1)
+            self.vis_t = self._vis.view(n, 1)
+        # bookkeeping for backward(): which slices of the flat gradient go to which parameter
+        slices = []
+        for net_id, nn_ in enumerate([net] + ([net1] if net1 is not None else [])):
+            off = 0
+            for p in nn_.parameters():
+                slices.append((net_id, off, p.numel(), p.shape, p.requires_grad))
+                off += p.numel()
+        self._param_slices = slices
+        return loss
+
+    def _trainable(self) -> List[torch.nn.Parameter]:
+        ps = list(self.net.parameters()) + (list(self.net_1.parameters()) if self.net_1 is not None else [])
+        return [p for p in ps if p.requires_grad]
+
+    # ---- the reference's hot-path methods -----------------------------------------------------
+    def fwd_computing_loss_2d(self, loss_mode="MSE"):
+        if loss_mode != "MSE":
+            raise NotImplementedError("only the 'MSE' loss mode (the one the reference trains with) is implemented")
+        assert self.x_f is not None and self.y_f is not None
+        params = self._trainable()
+        if torch.is_grad_enabled() and params:
+            self.loss = _StepFn.apply(self, *params)
+        else:
+            self.loss = self._launch_step()
+        return self.loss, [self.loss_e, self.loss_b]
+
+    def _equations(self, x, y):
+        x = _dev_f32(x, self.device); y = _dev_f32(y, self.device)
+        n = x.numel()
+        res = torch.empty(4 * n, dtype=torch.float32, device=self.device)
+        e = torch.empty(n, dtype=torch.float32, device=self.device) if self.HAS_EVM else None
+        vis = torch.empty(n, dtype=torch.float32, device=self.device) if self.HAS_EVM else None
+        vtm_in = None
+        if self.HAS_EVM:
+            if self.vis_t_minus is not None and self.vis_t_minus.numel() == n:
+                vtm_in = self.vis_t_minus
+            vtm_out = torch.empty(n, dtype=torch.float32, device=self.device)
+        self._ctx.residuals(self.net.flat_params().data_ptr(), self.net_1.flat_params().data_ptr() if self.HAS_EVM else None,
+                            x.data_ptr(), y.data_ptr(), vtm_in.data_ptr() if vtm_in is not None else None,
+                            vtm_out.data_ptr() if self.HAS_EVM else None, n, self._phys(n), res.data_ptr(),
+                            e.data_ptr() if e is not None else None, vis.data_ptr() if vis is not None else None, self._stream())
+        if self.HAS_EVM:
+            self.vis_t_minus = vtm_out  # the reference overwrites the lag state on every call (ev :334)
+            self.evm = e.view(n, 1)
+            self.vis_t = vis.view(n, 1)
+        return [res[k * n:(k + 1) * n].view(n, 1) for k in range(4)]
+
+    def predict(self, net_params, X):
+        x, y = X
+        return self.neural_net_u(x, y)
+
+    # ---- training loops ----------------------------------------------------------------------
+    def train(self, num_epoch=1, lr=1e-4, optimizer=None, scheduler=None, batchsize=None):
+        if self.opt is not None:
+            self.opt.param_groups[0]["lr"] = lr
+        else:
+            self.opt = torch.optim.Adam(params=self.net.parameters(), lr=lr)
+        return self.solve_Adam(self.fwd_computing_loss_2d, num_epoch, batchsize, scheduler)
+
+    def get_runtime_stats(self, epoch_id, num_epoch):
+        now = time.time()
+        if not hasattr(self, "_epoch_start_wall"):
+            return {}
+        elapsed = now - self._epoch_start_wall
+        avg = (epoch_id + 1) / elapsed if elapsed > 0 else 0.0
+        remain = num_epoch - (epoch_id + 1)
+        if self.vis_t is not None:
+            vm = float(self.vis_t.mean())
+            re_eff = 1.0 / (1.0 / self.Re + vm)
+        else:
+            vm = re_eff = float("nan")
+        return dict(avg_it_s=avg, eta_seconds=remain / avg if avg > 0 else float("inf"), vis_t_mean=vm, Re_eff=re_eff)
+
+    def print_log(self, loss, losses, epoch_id, num_epoch):
+        lr = self.opt.param_groups[0]["lr"]
+        now = time.time()
+        start = getattr(self, "_epoch_start_wall", now)
+        it_s = (epoch_id + 1) / max(now - start, 1e-9)
+        n_pts = (self.x_f.numel() if self.x_f is not None else 0) + (self.x_b.numel() if self.x_b is not None else 0)
+        msg = (f"[{self.current_stage}] epoch {epoch_id + 1}/{num_epoch} lr={lr:.2e} loss={float(loss):.4e} "
+               f"eq1={float(self.loss_eq1):.3e} eq2={float(self.loss_eq2):.3e} eq3={float(self.loss_eq3):.3e}")
+        if self.HAS_EVM:
+            st = self.get_runtime_stats(epoch_id, num_epoch)
+            msg += f" eq4={float(self.loss_eq4):.3e} Re_eff={st.get('Re_eff', float('nan')):.1f} alpha_evm={self.alpha_evm}"
+        msg += f" bc={float(self.loss_b):.3e} it/s={it_s:.2f} throughput={it_s * n_pts:.1f} pts/s"
+        print(msg)
+        if self.tb_writer is not None:
+            gs = self.global_step
+            self.tb_writer.add_scalar("loss/total", float(loss), gs)
+            self.tb_writer.add_scalar("loss/eq", float(self.loss_e), gs)
+            self.tb_writer.add_scalar("loss/bc", float(self.loss_b), gs)
+            self.tb_writer.add_scalar("lr", lr, gs)
+
+    # ---- evaluation / checkpoint ---------------------------------------
+    def _errors(self, x, y, u, v, p):
+        x_t, y_t, u_t, v_t, p_t = [np.asarray(a).reshape(-1, 1) for a in (x, y, u, v, p)]
+        outs = self.neural_net_u(torch.as_tensor(x_t), torch.as_tensor(y_t))
+        u_p, v_p, p_p = [o.detach().cpu().numpy().reshape(-1, 1) for o in outs[:3]]
+        e_p = outs[3].detach().cpu().numpy().reshape(-1, 1) if len(outs) > 3 else None
+        mask = ~np.isnan(p_t)
+        eu = 100 * np.linalg.norm(u_t - u_p, 2) / np.linalg.norm(u_t, 2)
+        ev = 100 * np.linalg.norm(v_t - v_p, 2) / np.linalg.norm(v_t, 2)
+        ep = 100 * np.linalg.norm(p_t[mask] - p_p[mask], 2) / np.linalg.norm(p_t[mask], 2)
+        return (eu, ev, ep), (u_p, v_p, p_p, e_p)
+
+    def evaluate(self, x, y, u, v, p):
+        (eu, ev, ep), _ = self._errors(x, y, u, v, p)
+        if self.rank == 0:
+            print("------------------------")
+            print("Error u: %.2f %%" % eu)
+            print("Error v: %.2f %%" % ev)
+            print("Error p: %.2f %%" % ep)
+        return eu, ev, ep
+
+    def test(self, x, y, u, v, p, loop=None, save_dir=None):
+        import scipy.io
+        (eu, ev, ep), (u_p, v_p, p_p, e_p) = self._errors(x, y, u, v, p)
+        if self.rank == 0:
+            print("------------------------")
+            print("Error u: %.3f %%" % eu)
+            print("Error v: %.3f %%" % ev)
+            print("Error p: %.3f %%" % ep)
+            print("------------------------")
+            side = int(round(np.sqrt(u_p.size)))  # 257 for the 256 files, 385 for cavity_Re4000_384 (the reference hard-codes 257)
+            shp = (side, side) if side * side == u_p.size else (-1, 1)
+            d = {"U_pred": u_p.reshape(shp), "V_pred": v_p.reshape(shp), "P_pred": p_p.reshape(shp), "error_u": eu,
+                 "error_v": ev, "error_p": ep, "lam_bcs": self.alpha_b, "lam_equ": self.alpha_e}
+            if e_p is not None:
+                d["E_pred"] = e_p.reshape(shp)
+            save_dir = save_dir or f"./results/Re{self.Re}/test_result"
+            os.makedirs(save_dir, exist_ok=True)
+            scipy.io.savemat(os.path.join(save_dir, f"cavity_result_loop_{loop}.mat"), d)
+        return eu, ev, ep
+
+    def _save_dir(self, directory, N_HLayer, N_neu, N_f):
+        raise NotImplementedError
+
+    def save(self, filename, directory=None, N_HLayer=None, N_neu=None, N_f=None):
+        out = self._save_dir(directory or os.getcwd(), N_HLayer, N_neu, N_f)
+        os.makedirs(out, exist_ok=True)
+        # clones: the parameters are views into one flat buffer; save plain per-tensor storages
+        torch.save({k: v.detach().clone() for k, v in self.net.state_dict().items()}, out + filename)
+        if self.net_1 is not None:
+            torch.save({k: v.detach().clone() for k, v in self.net_1.state_dict().items()}, out + filename + "_evm")
+        return out
