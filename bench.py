@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the PINN training hot path (BASELINE.json): collocation points / s for one
+residual-loss + weight-gradient evaluation, and full Adam steps / s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ev|ns] [--n-f N]
+
+Workload at every N (weak scaling): ev-NSFnet Re=2000 (main net 2-80x6-3, EVM net 2-40x4-1, EVM frozen
+as on 9 999 of 10 000 steps), 1 000 000 synthetic uniform collocation points PER GPU + the reference's
+2052 boundary points (sharded), fp32.  One "step" = one `nsf_step` (+ the gradient all-reduce when
+N > 1).  `--workload ns` runs BASELINE config[1] (NSFnet 4x120, Re=1000, 1M points) instead.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline` (dominant kernel, timed by
+CUDA events inside the library on the launching stream), `cpu_baseline` (the autograd port of the
+reference timed on this box's host cores), `adam_steps_per_s`, `e2e` (public solver API with host
+buffers), `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_PT = {"ev": 976_400.0, "ns": 1_305_840.0}      # algorithmic (5-stream) fwd + reverse
+EXEC_FLOPS_PER_PT = {"ev": 30 * 80 * 80 * 5 * 0.8 + 9840.0, "ns": 30 * 120 * 120 * 3 * 0.8}  # 4 streams carried (laplacian merged)
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(workload, n_f, steps, warmup):
+    """The reference's algorithm (oracle/autograd_port.py: torch modules + 7 autograd.grad sweeps + backward +
+    Adam, pinned to the reference by tests/golden) on the host cores."""
+    from oracle.autograd_port import time_reference_step
+    sec, threads = time_reference_step(workload, n_f, steps=steps, warmup=warmup)
+    return n_f / sec, sec, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_f = args.cpu_n_f
+    t0 = time.time()
+    pts_s, sec, threads = cpu_reference(args.workload, n_f, max(1, args.steps), max(1, args.warmup))
+    line = {"impl": "reference", "metric": "collocation_pts_per_s (residual + weight gradient)", "value": pts_s, "unit": "pts/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n_f_override=n_f),
+            "cpu_baseline": {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_f} collocation pts + 2052 boundary pts per step, full Adam step (N_f=1e6 does not fit host memory for the reference's retained graph)"},
+            "e2e": {"value": pts_s, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_f_override=None):
+    n_f = n_f_override if n_f_override is not None else args.n_f
+    if args.workload == "ev":
+        name = f"ev-NSFnet Re=2000 cavity, main 2-80x6-3 + EVM 2-40x4-1 (frozen), {n_f} uniform collocation pts/GPU + 2052 boundary pts"
+    else:
+        name = f"NSFnet Re=1000 cavity, 2-120x4-3, {n_f} uniform collocation pts/GPU + 2052 boundary pts"
+    return {"workload": name, "n_f_per_gpu": n_f, "n_b": 2052, "parallelism": f"dp{args.gpus} over points",
+            "l2": "flushed between timed iterations (256 MiB write)", "kernel_path": "ffma"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ev", choices=["ev", "ns"])
+    ap.add_argument("--n-f", type=int, default=1_000_000)
+    ap.add_argument("--cpu-n-f", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nsfnet_b200.cavity_data import cavity_boundary
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+
+    if args.workload == "ev":
+        from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+        torch.manual_seed(0)
+        P = PysicsInformedNeuralNetwork(Re=2000, layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=args.n_f * world,
+                                        alpha_evm=0.05, bc_weight=10, eq_weight=1, supervised_data_weight=0.0)
+    else:
+        from nsfnet_b200.nsfnet import PysicsInformedNeuralNetwork
+        torch.manual_seed(0)
+        P = PysicsInformedNeuralNetwork(Re=1000, layers=4, hidden_size=120, N_f=args.n_f * world, bc_weight=10, eq_weight=1)
+    if args.path:
+        P._ctx.set_path(args.path)
+    P.log_interval = 10 ** 9
+    P.checkpoints = False
+    P.set_boundary_data(cavity_boundary(513))
+    # every rank owns its own synthetic shard, generated on the device; the solver's sharding setter is
+    # bypassed for the collocation set because a W*1e6-point host array per rank is exactly what DP avoids
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n = args.n_f
+    x = torch.rand(n, device=dev, generator=g); y = torch.rand(n, device=dev, generator=g)
+    ws_save, rk_save = P.world_size, P.rank
+    P.world_size, P.rank = 1, 0
+    P.set_eq_training_data((x, y))
+    P.world_size, P.rank = ws_save, rk_save
+    P._n_f_global = n * world
+    if args.workload == "ev":
+        P.freeze_evm_net(0)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- metric (i): residual + weight gradient, inputs resident in HBM -------------------------
+    P._ctx.set_timing(True)
+    for _ in range(args.warmup):
+        P._launch_step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    launches = 0
+    sync_all()
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        P._launch_step()
+        ev[i][1].record()
+        launches += P._ctx.info()["launches"]
+        kern_ms.append(P._ctx.last_kernel_ms())      # syncs on the jet kernel's closing event only
+    sync_all()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms = float(tot.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- metric (ii): full Adam iterations (loss, backward, optimizer) ---------------------------
+    def adam_iter():
+        loss, _ = P.fwd_computing_loss_2d()
+        P.opt.zero_grad()
+        loss.backward()
+        P.opt.step()
+        return loss
+    for _ in range(3):
+        adam_iter()
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        adam_iter()
+    t1.record()
+    sync_all()
+    adam_ms = torch.tensor([t0.elapsed_time(t1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(adam_ms, op=dist.ReduceOp.MAX)
+    adam_steps_s = 1e3 / float(adam_ms.item())
+
+    # ---- e2e: public API with HOST buffers (pinned), H2D of the points + D2H of the loss every step
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.rand(n, 1).pin_memory(); hy = torch.rand(n, 1).pin_memory()
+
+        def e2e_iter():
+            P.set_eq_training_data((hx, hy))          # H2D of this step's points (+ the reference's init_vis_t)
+            P._n_f_global = n * world
+            loss, _ = P.fwd_computing_loss_2d()
+            P.opt.zero_grad()
+            loss.backward()
+            return float(loss)                          # D2H of the result
+        P.verbose = False
+        P.world_size, P.rank = ws_save, rk_save
+        shard = P._shard
+        P._shard = lambda total: (0, total)             # the host buffers ARE this rank's shard
+        for _ in range(2):
+            e2e_iter()
+        sync_all()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_iter()
+        sync_all()
+        e2e_s = (time.perf_counter() - w0) / args.steps
+        P._shard = shard
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world / float(t.item()), "unit": "pts/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4,
+               "ms_per_step": float(t.item()) * 1e3, "api": "set_eq_training_data(pinned host x,y) + fwd_computing_loss_2d() + loss.backward() + float(loss)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    bf16_burst, bf16_sust, hbm, how = read_peaks()
+    k_ms = float(np.mean(kern_ms))
+    flops = FLOPS_PER_PT[args.workload] * n
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    peak = 0.5 * bf16_sust          # dense TF32 = 1/2 of the measured sustained bf16 (kernel timed inside a long step)
+    info = P._ctx.info()
+    cfg = workload_config(args)
+    cfg["kernel_path"] = "ffma" if info["path"] == 1 else "tcgen05-3xtf32"
+    line = {"metric": "collocation_pts_per_s (residual + weight gradient)", "value": value, "unit": "pts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "adam_steps_per_s": adam_steps_s,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "collocation jet step (fwd jet + residuals + reverse)", "kernel_ms": k_ms,
+                         "kernel_share_of_step": k_ms / ms_per_step, "flops_per_pt_algorithmic": FLOPS_PER_PT[args.workload],
+                         "flops_per_pt_executed": EXEC_FLOPS_PER_PT[args.workload],
+                         "peak_note": f"0.5 x bf16_tflops_sustained ({how}); fp32 FFMA peak 148*128*2*1.965GHz = 74.5 TFLOP/s",
+                         "frac_of_ffma_peak": (EXEC_FLOPS_PER_PT[args.workload] * n / (k_ms * 1e-3) / 1e12) / 74.5,
+                         "hbm_algorithmic_GBps": 20.0 * n / (k_ms * 1e-3) / 1e9, "hbm_peak_GBps": hbm},
+            "gpu_launches": launches, "clocks": clocks}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        pts_s, sec, threads = cpu_reference(args.workload, args.cpu_n_f, 3, 1)
+        line["cpu_baseline"] = {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_n_f} collocation pts + 2052 boundary pts, 3 full Adam steps after 1 warm-up ({sec * 1e3:.0f} ms/step)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

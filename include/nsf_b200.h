@@ -110,6 +110,12 @@ int nsf_set_path(NsfCtx* ctx, int path);
  * [2]=kernel launches issued by the last nsf_* call, [3]=workspace bytes. */
 int nsf_get_info(NsfCtx* ctx, int64_t info[4]);
 
+/* Measurement hook (bench.py roofline): when enabled, nsf_step / nsf_residuals bracket their dominant
+ * kernel (the collocation jet kernel) with CUDA events on the caller's stream; nsf_last_kernel_ms
+ * synchronises on the closing event and returns the elapsed milliseconds of the last one. */
+int nsf_set_timing(NsfCtx* ctx, int enable);
+int nsf_last_kernel_ms(NsfCtx* ctx, float* ms);
+
 /* One `fwd_computing_loss_2d()` + `loss.backward()`:
  *   ev-NSFnet/pinn_solver.py:372-428 + :468-469 (DDP all-reduce excluded), i.e.
  *   neural_net_u on the blocks (:280-288), neural_net_equations on the collocation points

@@ -20,6 +20,7 @@ NSF_MAX_BLOCKS = 2
 NSF_LOSS_SLOTS = 16
 
 EXPORTS = ["nsf_abi_version", "nsf_last_error", "nsf_create", "nsf_destroy", "nsf_set_path", "nsf_get_info",
+           "nsf_set_timing", "nsf_last_kernel_ms",
            "nsf_step", "nsf_residuals", "nsf_forward", "nsf_adam", "nsf_selftest_umma"]
 
 
@@ -59,6 +60,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nsf_set_path.argtypes = [vp, C.c_int]
     lib.nsf_get_info.restype = C.c_int
     lib.nsf_get_info.argtypes = [vp, C.POINTER(i64 * 4)]
+    lib.nsf_set_timing.restype = C.c_int
+    lib.nsf_set_timing.argtypes = [vp, C.c_int]
+    lib.nsf_last_kernel_ms.restype = C.c_int
+    lib.nsf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.nsf_step.restype = C.c_int
     lib.nsf_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(NsfDataBlock), i32, C.POINTER(NsfPhysics),
                              vp, vp, vp, vp, vp, vp, vp]
@@ -130,6 +135,14 @@ class Context:
         arr = (C.c_int64 * 4)()
         check(self.lib, self.lib.nsf_get_info(self.h, C.byref(arr)))
         return dict(sms=arr[0], path=arr[1], launches=arr[2], workspace_bytes=arr[3])
+
+    def set_timing(self, enable: bool):
+        check(self.lib, self.lib.nsf_set_timing(self.h, 1 if enable else 0))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(self.lib, self.lib.nsf_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def step(self, params_main, params_evm, x, y, w, vtm_in, vtm_out, n_f, blocks, phys, grad_main, grad_evm,
              loss_parts, residuals_out=None, e_out=None, vis_t_out=None, stream=None):

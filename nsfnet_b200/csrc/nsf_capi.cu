@@ -105,6 +105,10 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   if (!ctx) return NSF_OK;
   free_net(ctx->main); free_net(ctx->evm);
   nsf_rt_free(ctx->e_buf); nsf_rt_free(ctx->ebar_buf);
+#ifndef NSF_EMU
+  if (ctx->ev0) cudaEventDestroy((cudaEvent_t)ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy((cudaEvent_t)ctx->ev1);
+#endif
   delete ctx;
   return NSF_OK;
 }
@@ -121,6 +125,38 @@ extern "C" int nsf_get_info(NsfCtx* ctx, int64_t info[4]) {
   info[0] = ctx->sms; info[1] = 1; info[2] = ctx->launches; info[3] = ctx->ws_bytes;
   return NSF_OK;
 }
+
+#ifdef NSF_EMU
+static int time_mark(NsfCtx*, int, nsf_stream_t) { return NSF_OK; }
+extern "C" int nsf_set_timing(NsfCtx* ctx, int enable) { if (!ctx) return NSF_E_ARG; ctx->timing = enable; return NSF_OK; }
+extern "C" int nsf_last_kernel_ms(NsfCtx*, float* ms) { if (ms) *ms = 0.f; return NSF_OK; }
+#else
+static int time_mark(NsfCtx* ctx, int which, nsf_stream_t st) {
+  if (!ctx->timing) return NSF_OK;
+  NSF_CUDA_OK(cudaEventRecord((cudaEvent_t)(which ? ctx->ev1 : ctx->ev0), st));
+  if (which) ctx->timed = 1;
+  return NSF_OK;
+}
+extern "C" int nsf_set_timing(NsfCtx* ctx, int enable) {
+  if (!ctx) { nsf_set_error("nsf_set_timing: null context"); return NSF_E_ARG; }
+  if (enable && !ctx->ev0) {
+    cudaEvent_t a, b;
+    NSF_CUDA_OK(cudaEventCreate(&a));
+    NSF_CUDA_OK(cudaEventCreate(&b));
+    ctx->ev0 = a; ctx->ev1 = b;
+  }
+  ctx->timing = enable ? 1 : 0;
+  ctx->timed = 0;
+  return NSF_OK;
+}
+extern "C" int nsf_last_kernel_ms(NsfCtx* ctx, float* ms) {
+  if (!ctx || !ms) { nsf_set_error("nsf_last_kernel_ms: null argument"); return NSF_E_ARG; }
+  if (!ctx->timed) { nsf_set_error("nsf_last_kernel_ms: no timed kernel yet (nsf_set_timing + nsf_step first)"); return NSF_E_ARG; }
+  NSF_CUDA_OK(cudaEventSynchronize((cudaEvent_t)ctx->ev1));
+  NSF_CUDA_OK(cudaEventElapsedTime(ms, (cudaEvent_t)ctx->ev0, (cudaEvent_t)ctx->ev1));
+  return NSF_OK;
+}
+#endif
 
 static int ensure_cap(NsfCtx* ctx, long long n) {
   if (n <= ctx->cap) return NSF_OK;
@@ -204,7 +240,9 @@ extern "C" int nsf_residuals(NsfCtx* ctx, const float* params_main, const float*
   phys_args(a, ph, n);
   a.e_in = e_ptr; a.vtm_in = vtm_in; a.vtm_out = vtm_out; a.resid_out = residuals_out; a.vis_t_out = vis_t_out;
   a.scratch = nullptr; a.stash = nullptr;
+  NSF_TRY(time_mark(ctx, 0, st));
   NSF_TRY(nsf_ffma_launch(a, 4, grid_for(ctx, ctx->main, 4, n), st)); ctx->launches++;
+  NSF_TRY(time_mark(ctx, 1, st));
   return NSF_OK;
 }
 
@@ -270,7 +308,9 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     a.e_in = e_ptr; a.vtm_in = vtm_in; a.vtm_out = vtm_out; a.w = w;
     a.resid_out = residuals_out; a.vis_t_out = vis_t_out;
     a.ebar_out = evm_train ? ctx->ebar_buf : nullptr;
+    NSF_TRY(time_mark(ctx, 0, st));
     NSF_TRY(nsf_ffma_launch(a, 4, grids[0], st)); ctx->launches++;
+    NSF_TRY(time_mark(ctx, 1, st));
   }
   for (int b = 0; b < n_blocks; ++b) {
     const NsfDataBlock& k = blocks[b];

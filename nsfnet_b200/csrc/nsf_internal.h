@@ -61,6 +61,10 @@ struct NsfCtx {
   float* ebar_buf = nullptr;  // [cap] d(loss)/d(e)
   long long cap = 0;
   void* umma = nullptr;  // tcgen05 path state (nsf_umma.cu)
+  int timing = 0;        // bracket the dominant kernel with events (nsf_set_timing)
+  void* ev0 = nullptr;
+  void* ev1 = nullptr;
+  int timed = 0;
 };
 
 // nsf_ffma.cu ------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ class SolverBase:
     tb_writer = None
     global_step = 0
     HAS_EVM = False
+    verbose = True
 
     # ------------------------------------------------------------------------------------
     def _init_common(self, Re, layers, hidden_size, N_f, bc_weight, eq_weight, num_ins, num_outs, learning_rate,
@@ -154,7 +155,7 @@ class SolverBase:
         s, e = self._shard(total)
         self.x_b, self.y_b, self.u_b, self.v_b = [_dev_f32(np.asarray(a)[s:e], self.device) for a in X[:4]]
         self._n_b_global = total
-        if self.rank == 0:
+        if self.rank == 0 and self.verbose:
             print(f"GPU {self.rank}: Processing {e - s} boundary points out of {total} total")
 
     def set_eq_training_data(self, X=None, time=False, weights=None):
@@ -176,7 +177,7 @@ class SolverBase:
         self._resid = torch.empty(4 * n, dtype=torch.float32, device=self.device)
         self._e = torch.empty(n, dtype=torch.float32, device=self.device)
         self._vis = torch.empty(n, dtype=torch.float32, device=self.device)
-        if self.rank == 0:
+        if self.rank == 0 and self.verbose:
             print(f"GPU {self.rank}: Processing {e - s} equation points out of {total} total")
         if self.HAS_EVM:
             self.init_vis_t()

@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI and through the solver classes) with the CPU oracle and
+with the reference's own golden vectors.  Tolerance: north_star's 1e-5 relative (norm-wise, per
+tensor); measured values are ~1e-6 for the FP32 path."""
+import os
+
+import numpy as np
+import pytest
+
+from nsfnet_b200 import _capi
+from oracle import jet_numpy as J
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gu():
+    import torch
+    assert torch.cuda.is_available()
+    from tests import gpu_util
+    return gpu_util
+
+
+def _bc(nb):
+    return 10. / nb
+
+
+@pytest.mark.parametrize("L,H,n,nb", [(3, 16, 70, 21), (6, 80, 1333, 132), (4, 120, 650, 33), (2, 10, 37, 5), (1, 8, 9, 3),
+                                      (10, 50, 301, 64), (6, 20, 95, 1)])
+@pytest.mark.parametrize("has_evm", [False, True])
+def test_step_matches_oracle(gu, L, H, n, nb, has_evm):
+    rng = np.random.default_rng(L * 100 + H)
+    md, ed = J.NetDesc(2, 3, L, H), J.NetDesc(2, 1, 4, 40)
+    pm, pe = J.init_params(md, 1) * 1.5, J.init_params(ed, 2)
+    x, y = rng.random(n).astype(np.float32), rng.random(n).astype(np.float32)
+    xb, yb, ub, vb = [rng.random(nb).astype(np.float32) for _ in range(4)]
+    w = (0.5 + rng.random(n)).astype(np.float32)
+    vtm = (rng.random(n) * 0.02).astype(np.float32)
+    cs = 1.3 if has_evm else 1.0
+    phys = J.Physics(Re=1000., alpha_b=10., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
+    r = J.step(pm, md, phys, x, y, xb, yb, ub, vb, evm_flat=pe if has_evm else None, evm_desc=ed if has_evm else None, w=w,
+               vis_t_minus=vtm if has_evm else None)
+    abi = gu.Abi((2, 3, L, H), (2, 1, 4, 40) if has_evm else None)
+    cp = _capi.physics(1000., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
+    o = abi.step(pm, cp, x, y, blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)], params_evm=pe if has_evm else None, w=w,
+                 vtm_in=vtm if has_evm else None)
+    assert gu.rel(o["grad_main"], r.grad_main) < TOL
+    for k in range(4 if has_evm else 3):
+        assert gu.rel(o["resid"][k], r.eq[k]) < TOL
+        assert abs(o["loss_parts"][k] / n - r.loss_eq[k]) < TOL * r.loss_eq[k]
+    assert o["loss_parts"][5] == n
+    assert abs((o["loss_parts"][6] + o["loss_parts"][7]) / nb - r.loss_b) < TOL * r.loss_b
+    if has_evm:
+        assert gu.rel(o["grad_evm"], r.grad_evm) < TOL
+        assert gu.rel(o["e"], r.e) < TOL
+        assert gu.rel(o["vis_t"], r.vis_t) < 1e-6
+        assert gu.rel(o["vtm_out"], r.vis_t_minus_next) < TOL
+
+
+def test_golden_ev_lag(gu, golden_dir):
+    """Reference outputs (ev-NSFnet 6x80+4x40, three consecutive steps with the lagged viscosity)."""
+    g = np.load(os.path.join(golden_dir, "ev_re2000_lag.npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb, n = xb.size, g["xf"].size
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40))
+    vtm = g["vis_t_minus_init"]
+    for k in range(int(g["steps"])):
+        cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
+        o = abi.step(g[f"params_main_{k}"], cp, g["xf"], g["yf"], blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)],
+                     params_evm=g[f"params_evm_{k}"], vtm_in=vtm)
+        assert gu.rel(o["grad_main"], g[f"grad_main_{k}"]) < TOL
+        assert gu.rel(o["vis_t"], g[f"vis_t_{k}"]) < 1e-6
+        assert gu.rel(o["e"], g[f"e_{k}"]) < TOL
+        for i in range(4):
+            assert gu.rel(o["resid"][i], g[f"eq{i+1}_{k}"]) < TOL
+        lp = o["loss_parts"]
+        loss = 10. * (lp[6] + lp[7]) / nb + (lp[0] + lp[1] + lp[2] + 0.1 * lp[3]) / n
+        assert abs(loss - float(g[f"loss_{k}"])) < TOL * float(g[f"loss_{k}"])
+        vtm = o["vtm_out"]
+
+
+def test_golden_supervised_scale_and_sdf_unfrozen(gu, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ev_re3000_scale_sup.npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb = xb.size
+    s = g["sup"]
+    ns, nps, a_s = s.shape[0], int(np.isfinite(s[:, 4]).sum()), float(g["alpha_s"])
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40))
+    cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True, coord_scale=float(g["coord_scale"]))
+    o = abi.step(g["params_main_0"], cp, g["xf"], g["yf"],
+                 blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.), (s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 4], a_s / ns, a_s / ns, a_s / nps)],
+                 params_evm=g["params_evm_0"], vtm_in=g["vis_t_minus_init"])
+    assert gu.rel(o["grad_main"], g["grad_main_0"]) < TOL
+    lp = o["loss_parts"]
+    assert lp[13] == nps
+    assert abs((lp[10] + lp[11]) / ns + lp[12] / nps - float(g["loss_s_0"])) < TOL * float(g["loss_s_0"])
+
+    g = np.load(os.path.join(golden_dir, "ev_re5000_sdf_unfrozen.npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb = xb.size
+    cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True, evm_trainable=True)
+    o = abi.step(g["params_main_0"], cp, g["xf"], g["yf"], blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)],
+                 params_evm=g["params_evm_0"], w=g["w"], vtm_in=g["vis_t_minus_init"])
+    assert gu.rel(o["grad_main"], g["grad_main_0"]) < TOL
+    assert gu.rel(o["grad_evm"], g["grad_evm_0"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["ns_re100_init", "ns_re1000_x2p5"])
+def test_golden_ns(gu, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb, n = xb.size, g["xf"].size
+    abi = gu.Abi((2, 3, 4, 120))
+    o = abi.step(g["params"], _capi.physics(float(g["Re"])), g["xf"], g["yf"], blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)])
+    assert gu.rel(o["grad_main"], g["grad"]) < TOL
+    for i in range(3):
+        assert gu.rel(o["resid"][i], g[f"eq{i+1}"]) < TOL
+        assert abs(o["loss_parts"][i] / n - g["loss_eq"][i]) < TOL * g["loss_eq"][i]
+    # value forward (neural_net_u) against the reference's own outputs
+    import torch
+    out = torch.empty((n, 3), device="cuda")
+    pm, x, y = gu.dev(g["params"]), gu.dev(g["xf"]), gu.dev(g["yf"])
+    abi.ctx.forward(0, pm.data_ptr(), x.data_ptr(), y.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert gu.rel(out.cpu().numpy(), g["uvp"]) < TOL
+
+
+def test_edge_cases(gu):
+    import torch
+    md = J.NetDesc(2, 3, 2, 8)
+    pm = J.init_params(md, 0)
+    abi = gu.Abi((2, 3, 2, 8))
+    o = abi.step(pm, _capi.physics(100.), np.zeros(0, np.float32), np.zeros(0, np.float32), blocks=[])
+    assert np.all(o["grad_main"] == 0) and np.all(o["loss_parts"] == 0)
+    # boundary only
+    xb, yb, ub, vb = J.cavity_boundary(9)
+    o = abi.step(pm, _capi.physics(100.), np.zeros(0, np.float32), np.zeros(0, np.float32), blocks=[(xb, yb, ub, vb, None, 1., 1., 0.)])
+    out, acts = J.mlp_forward(J.unpack(pm, md), np.stack([xb, yb], 1))
+    assert abs(o["loss_parts"][6] - np.sum((out[:, 0] - ub) ** 2)) < 1e-5 * o["loss_parts"][6]
+    with pytest.raises(_capi.NsfError):
+        _capi.Context(abi.lib, 0, (3, 3, 2, 8))
+    with pytest.raises(_capi.NsfError):
+        _capi.Context(abi.lib, 0, (2, 3, 2, 200))
+    with pytest.raises(_capi.NsfError):
+        abi.step(pm, _capi.physics(100., has_evm=True), np.zeros(4, np.float32), np.zeros(4, np.float32))
+    # more boundary tiles than collocation tiles: rows the first launch does not own must be zeroed
+    rng = np.random.default_rng(3)
+    x, y = rng.random(40).astype(np.float32), rng.random(40).astype(np.float32)
+    nb = 40000
+    xb, yb, ub, vb = [rng.random(nb).astype(np.float32) for _ in range(4)]
+    r = J.step(pm, md, J.Physics(Re=100.), x, y, xb, yb, ub, vb)
+    o = abi.step(pm, _capi.physics(100.), x, y, blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)])
+    assert gu.rel(o["grad_main"], r.grad_main) < TOL
+
+
+def test_full_size_properties(gu):
+    """BASELINE config sizes (1M points, ev 6x80 + 4x40): size-independent properties.
+    (1) determinism: two runs are bit-identical; (2) additivity / data-parallel identity: the gradient
+    on the union equals the sum of the shard gradients when both use the global normaliser;
+    (3) nsf_residuals reproduces the residuals of nsf_step bit for bit; (4) a 50k-point prefix matches the oracle."""
+    import torch
+    n = 1_000_000
+    md, ed = J.NetDesc(2, 3, 6, 80), J.NetDesc(2, 1, 4, 40)
+    pm, pe = J.init_params(md, 5), J.init_params(ed, 6)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.rand(n, device="cuda", generator=g); y = torch.rand(n, device="cuda", generator=g)
+    vtm = torch.rand(n, device="cuda", generator=g) * 0.02
+    xb, yb, ub, vb = J.cavity_boundary(513)
+    nb = xb.size
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40))
+    blocks = [(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)]
+    cp = _capi.physics(2000., alpha_evm=0.05, has_evm=True, n_f_norm=n)
+    a = abi.step(pm, cp, x, y, blocks=blocks, params_evm=pe, vtm_in=vtm)
+    b = abi.step(pm, cp, x, y, blocks=blocks, params_evm=pe, vtm_in=vtm)
+    assert np.array_equal(a["grad_main"], b["grad_main"]) and np.array_equal(a["resid"], b["resid"])
+    h = n // 2 + 777
+    s1 = abi.step(pm, cp, x[:h].contiguous(), y[:h].contiguous(), blocks=blocks, params_evm=pe, vtm_in=vtm[:h].contiguous())
+    s2 = abi.step(pm, cp, x[h:].contiguous(), y[h:].contiguous(), blocks=[], params_evm=pe, vtm_in=vtm[h:].contiguous())
+    assert gu.rel(s1["grad_main"] + s2["grad_main"], a["grad_main"]) < 2e-6
+    assert abs((s1["loss_parts"][:6] + s2["loss_parts"][:6]) / a["loss_parts"][:6] - 1).max() < 1e-5
+    # residuals-only entry point
+    res = torch.empty(4 * n, device="cuda")
+    pmd, ped = gu.dev(pm), gu.dev(pe)
+    abi.ctx.residuals(pmd.data_ptr(), ped.data_ptr(), x.data_ptr(), y.data_ptr(), vtm.data_ptr(), None, n, cp, res.data_ptr(), None, None,
+                      torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(res.cpu().numpy().reshape(4, n), a["resid"])
+    # oracle on a prefix
+    m = 50_000
+    cpm = _capi.physics(2000., alpha_evm=0.05, has_evm=True)
+    o = abi.step(pm, cpm, x[:m].contiguous(), y[:m].contiguous(), blocks=blocks, params_evm=pe, vtm_in=vtm[:m].contiguous())
+    r = J.step(pm, md, J.Physics(Re=2000., alpha_evm=0.05, has_evm=True), x[:m].cpu().numpy(), y[:m].cpu().numpy(), xb, yb, ub, vb,
+               evm_flat=pe, evm_desc=ed, vis_t_minus=vtm[:m].cpu().numpy())
+    assert gu.rel(o["grad_main"], r.grad_main) < TOL
+    assert abs(sum(o["loss_parts"][:3]) / m - sum(r.loss_eq[:3])) < TOL * sum(r.loss_eq[:3])

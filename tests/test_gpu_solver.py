@@ -1,0 +1,135 @@
+"""The drop-in solver classes on the GPU: API semantics of the reference (loss.backward() filling
+p.grad, freeze / unfreeze, lagged viscosity hand-off) and loss-curve tracking against curves recorded
+from the reference's own training loops (tests/golden/curve_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jet_numpy as J
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def load_flat(net, flat):
+    import torch
+    off = 0
+    with torch.no_grad():
+        for p in net.parameters():
+            k = p.numel()
+            p.copy_(torch.as_tensor(flat[off:off + k]).view(p.shape))
+            off += k
+    assert off == flat.size
+
+
+def flat_grad(net):
+    import torch
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()]).cpu().numpy()
+
+
+def test_ev_solver_step_and_freeze_semantics():
+    import torch
+    from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+    torch.manual_seed(1)
+    P = PysicsInformedNeuralNetwork(Re=2000, layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=3000, alpha_evm=0.05,
+                                    bc_weight=10, eq_weight=1, supervised_data_weight=0.0)
+    assert sorted(P.net.state_dict().keys())[0] == "layers.layer_0.bias"
+    rng = np.random.default_rng(0)
+    xb, yb, ub, vb = J.cavity_boundary(65)
+    xf, yf = rng.random(3000).astype(np.float32), rng.random(3000).astype(np.float32)
+    P.set_boundary_data((xb.reshape(-1, 1), yb.reshape(-1, 1), ub.reshape(-1, 1), vb.reshape(-1, 1)))
+    P.set_eq_training_data((xf.reshape(-1, 1), yf.reshape(-1, 1)))
+    md, ed = J.NetDesc(2, 3, 6, 80), J.NetDesc(2, 1, 4, 40)
+    vtm = P.vis_t_minus.cpu().numpy().copy()
+    for unfrozen in (False, True):
+        (P.defreeze_evm_net if unfrozen else P.freeze_evm_net)(0)
+        pm = P.net.flat_params().cpu().numpy().copy(); pe = P.net_1.flat_params().cpu().numpy().copy()
+        loss, (loss_e, loss_b) = P.fwd_computing_loss_2d()
+        P.opt.zero_grad()
+        loss.backward()
+        r = J.step(pm, md, J.Physics(Re=2000., alpha_evm=0.05, has_evm=True, evm_trainable=unfrozen), xf, yf, xb, yb, ub, vb,
+                   evm_flat=pe, evm_desc=ed, vis_t_minus=vtm)
+        assert abs(float(loss) - r.loss) < 1e-5 * r.loss
+        assert abs(float(loss_e) - r.loss_e) < 1e-5 * r.loss_e and abs(float(loss_b) - r.loss_b) < 1e-5 * r.loss_b
+        assert rel(flat_grad(P.net), r.grad_main) < 1e-5
+        if unfrozen:
+            assert rel(flat_grad(P.net_1), r.grad_evm) < 1e-5
+        else:
+            assert all(p.grad is None for p in P.net_1.parameters())
+        assert rel(P.eq4_pred.cpu().numpy(), r.eq[3]) < 1e-5 and P.eq4_pred.shape == (3000, 1)
+        assert rel(P.evm.cpu().numpy(), r.e) < 1e-5
+        vtm = P.vis_t_minus.cpu().numpy().copy()          # alpha*|e| of THIS step feeds the next (ev :334)
+        assert rel(vtm, r.vis_t_minus_next) < 1e-5
+        P.opt.step()
+    # scaling through autograd: d(3*loss) = 3 * d(loss) on identical weights and lag state
+    P.freeze_evm_net(0)
+    v0 = torch.as_tensor(vtm).cuda()
+    P.vis_t_minus = v0.clone()
+    loss, _ = P.fwd_computing_loss_2d(); P.opt.zero_grad(); loss.backward(); g1 = flat_grad(P.net)
+    P.vis_t_minus = v0.clone()
+    loss, _ = P.fwd_computing_loss_2d(); P.opt.zero_grad(); (3.0 * loss).backward(); g3 = flat_grad(P.net)
+    assert rel(g3, 3.0 * g1) < 1e-6
+    # neural_net_u shapes of the reference (ev :280-288) and parity with the torch module forward
+    u, v, p, e = P.neural_net_u(torch.as_tensor(xf).view(-1, 1), torch.as_tensor(yf).view(-1, 1))
+    assert u.shape == (3000,) and v.shape == (3000,) and p.shape == (3000, 1) and e.shape == (3000, 1)
+    with torch.no_grad():
+        ref = P.net(torch.stack([torch.as_tensor(xf), torch.as_tensor(yf)], 1).cuda())
+    assert rel(u.cpu().numpy(), ref[:, 0].cpu().numpy()) < 1e-5
+    eqs = P.neural_net_equations(torch.as_tensor(xf).view(-1, 1), torch.as_tensor(yf).view(-1, 1))
+    assert len(eqs) == 4 and eqs[0].shape == (3000, 1)
+
+
+def test_ns_curves_track_reference(golden_dir):
+    """NSFnet Re=100 / Re=1000: 200 Adam steps from the reference's initial weights; the loss curve
+    recorded from the reference's own solve_Adam body must be tracked (BASELINE.json: "loss curves must track")."""
+    import torch
+    from nsfnet_b200.nsfnet import PysicsInformedNeuralNetwork
+    for name in ("curve_ns_re100", "curve_ns_re1000"):
+        g = np.load(os.path.join(golden_dir, name + ".npz"))
+        P = PysicsInformedNeuralNetwork(Re=float(g["Re"]), layers=4, hidden_size=120, N_f=g["xf"].size, bc_weight=10, eq_weight=1)
+        load_flat(P.net, g["params"])
+        xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+        P.set_boundary_data((xb, yb, ub, vb)); P.set_eq_training_data((g["xf"], g["yf"]))
+        P.opt.param_groups[0]["lr"] = float(g["lr"])
+        curve = []
+        for k in range(int(g["steps"])):
+            loss, _ = P.fwd_computing_loss_2d()
+            loss.backward(); P.opt.step(); P.opt.zero_grad()
+            if k % int(g["every"]) == 0:
+                curve.append(float(loss))
+        curve = np.array(curve)
+        err = np.abs(curve - g["curve"]) / g["curve"]
+        print(name, "max rel curve deviation", err.max(), "first", err[0])
+        assert err[0] < 1e-5
+        assert err.max() < 2e-2, err
+
+
+def test_ev_curve_tracks_reference(golden_dir):
+    import torch
+    from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+    g = np.load(os.path.join(golden_dir, "curve_ev_re2000.npz"))
+    P = PysicsInformedNeuralNetwork(Re=float(g["Re"]), layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=g["xf"].size,
+                                    alpha_evm=float(g["alpha_evm"]), bc_weight=10, eq_weight=1, supervised_data_weight=0.0)
+    load_flat(P.net, g["params_main"]); load_flat(P.net_1, g["params_evm"])
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    P.set_boundary_data((xb, yb, ub, vb)); P.set_eq_training_data((g["xf"], g["yf"]))
+    P.log_interval = 10 ** 9
+    P.checkpoints = False
+    curve = []
+    orig = P.fwd_computing_loss_2d
+
+    def rec():
+        out = orig()
+        curve.append(float(out[0]))
+        return out
+    P.opt.param_groups[0]["lr"] = float(g["lr"])
+    P.solve_Adam(rec, int(g["steps"]))
+    c = np.array(curve[::int(g["every"])])
+    err = np.abs(c - g["curve"]) / g["curve"]
+    print("ev curve max rel deviation", err.max())
+    assert err[0] < 1e-5 and err.max() < 2e-2, err
