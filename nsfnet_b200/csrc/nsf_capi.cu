@@ -106,6 +106,7 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   free_net(ctx->main); free_net(ctx->evm);
   nsf_rt_free(ctx->e_buf); nsf_rt_free(ctx->ebar_buf);
 #ifndef NSF_EMU
+  nsf_umma_free(ctx);
   if (ctx->ev0) cudaEventDestroy((cudaEvent_t)ctx->ev0);
   if (ctx->ev1) cudaEventDestroy((cudaEvent_t)ctx->ev1);
 #endif
@@ -113,16 +114,47 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   return NSF_OK;
 }
 
+// kernel family the next collocation launch uses: 1 = FFMA, 2 = tcgen05
+static int effective_path(const NsfCtx* ctx) {
+#ifdef NSF_EMU
+  return 1;
+#else
+  if (ctx->path == 1) return 1;
+  return nsf_umma_supported(ctx->main.g) ? 2 : 1;
+#endif
+}
+
 extern "C" int nsf_set_path(NsfCtx* ctx, int path) {
   if (!ctx || path < 0 || path > 2) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
-  if (path == 2) { nsf_set_error("tcgen05 path not available in this build for this shape"); return NSF_E_SHAPE; }
+#ifdef NSF_EMU
+  if (path == 2) { nsf_set_error("tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE; }
+#else
+  if (path == 2 && !nsf_umma_supported(ctx->main.g)) {
+    nsf_set_error("tcgen05 path covers hidden = 80 with 2..6 hidden layers; this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
+    return NSF_E_SHAPE;
+  }
+#endif
   ctx->path = path;
   return NSF_OK;
 }
 
 extern "C" int nsf_get_info(NsfCtx* ctx, int64_t info[4]) {
   if (!ctx || !info) { nsf_set_error("nsf_get_info: null argument"); return NSF_E_ARG; }
-  info[0] = ctx->sms; info[1] = 1; info[2] = ctx->launches; info[3] = ctx->ws_bytes;
+  info[0] = ctx->sms; info[1] = effective_path(ctx); info[2] = ctx->launches; info[3] = ctx->ws_bytes;
+  return NSF_OK;
+}
+
+// the collocation jet launch (step or residuals) on whichever kernel family is selected
+static int launch_jet(NsfCtx* ctx, NsfKernelArgs& a, const float* flat_main, int* grid, nsf_stream_t st) {
+#ifndef NSF_EMU
+  if (effective_path(ctx) == 2) {
+    NSF_TRY(nsf_umma_init(ctx));
+    return nsf_umma_launch(ctx, a, flat_main, grid, st, &ctx->launches);
+  }
+#endif
+  (void)flat_main;
+  NSF_TRY(nsf_ffma_launch(a, 4, *grid, st));
+  ctx->launches++;
   return NSF_OK;
 }
 
@@ -241,7 +273,8 @@ extern "C" int nsf_residuals(NsfCtx* ctx, const float* params_main, const float*
   a.e_in = e_ptr; a.vtm_in = vtm_in; a.vtm_out = vtm_out; a.resid_out = residuals_out; a.vis_t_out = vis_t_out;
   a.scratch = nullptr; a.stash = nullptr;
   NSF_TRY(time_mark(ctx, 0, st));
-  NSF_TRY(nsf_ffma_launch(a, 4, grid_for(ctx, ctx->main, 4, n), st)); ctx->launches++;
+  int gj = grid_for(ctx, ctx->main, 4, n);
+  NSF_TRY(launch_jet(ctx, a, params_main, &gj, st));
   NSF_TRY(time_mark(ctx, 1, st));
   return NSF_OK;
 }
@@ -272,6 +305,13 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   // grids of the launches that accumulate into the main net's gradient rows
   int grids[1 + NSF_MAX_BLOCKS];
   grids[0] = n_f > 0 ? grid_for(ctx, M, 4, n_f) : 0;
+#ifndef NSF_EMU
+  if (n_f > 0 && effective_path(ctx) == 2) {   // one persistent CTA per SM, a pair of 8-point tiles per iteration
+    NSF_TRY(nsf_umma_init(ctx));
+    const long long pairs = (n_f + 15) / 16;
+    grids[0] = (int)(pairs < ctx->sms ? pairs : ctx->sms);
+  }
+#endif
   for (int b = 0; b < n_blocks; ++b) grids[1 + b] = blocks[b].n > 0 ? grid_for(ctx, M, 1, blocks[b].n) : 0;
   int first = -1, rows_used = 0;
   for (int i = 0; i < 1 + n_blocks; ++i) {
@@ -309,7 +349,7 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     a.resid_out = residuals_out; a.vis_t_out = vis_t_out;
     a.ebar_out = evm_train ? ctx->ebar_buf : nullptr;
     NSF_TRY(time_mark(ctx, 0, st));
-    NSF_TRY(nsf_ffma_launch(a, 4, grids[0], st)); ctx->launches++;
+    NSF_TRY(launch_jet(ctx, a, params_main, &grids[0], st));
     NSF_TRY(time_mark(ctx, 1, st));
   }
   for (int b = 0; b < n_blocks; ++b) {

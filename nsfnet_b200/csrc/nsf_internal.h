@@ -80,6 +80,12 @@ int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, con
 int nsf_adam_launch(float* params, const float* grad, float* m, float* v, long long n, float lr, float b1, float b2,
                     float eps, float bc1, float bc2, float grad_scale, nsf_stream_t st);
 
+// nsf_umma_jet.cu (CUDA build only) ---------------------------------------------------------------
+int nsf_umma_supported(const NsfNetGeom& g);
+int nsf_umma_init(NsfCtx* ctx);
+void nsf_umma_free(NsfCtx* ctx);
+int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
+
 // flat parameter i of the packed image (host + device)
 NSF_HD float nsf_pack_value(const NsfNetGeom& g, const float* flat, int i) {
   const int H = g.H, HP = g.HP;

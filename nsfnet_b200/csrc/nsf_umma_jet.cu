@@ -1,0 +1,612 @@
+// tcgen05 jet kernel: the collocation step of the main net (2 -> 80 x L -> 3, L <= 6) with the hidden
+// layer contractions on the 5th-generation tensor cores, 3xTF32 split for fp32 fidelity.
+//
+// Orientation: TMEM lane = neuron, TMEM column = 4*point + stream (streams 0, x, y, laplacian), i.e. the
+// MMA is  D[neuron j, (p,s)] = sum_k W[j,k] * a_s[p,k]  with M = 128 (80 real rows), N = 4*P, K = 80.
+// An epilogue thread owns one neuron of a quarter of the tile's points: it reads its 4 stream values of a
+// point with ONE tcgen05.ld, applies the tanh jet on FFMA / MUFU and writes the next layer's operands.
+//
+// One CTA per SM (persistent), 9 warps:
+//   warps 0-7 : epilogue (warp w -> TMEM lane quadrant w & 3, points 4*(w >> 2) .. +3 of the tile)
+//   warp  8   : issuer (one lane): TMA bulk loads of the weight images, tcgen05.mma, tcgen05.commit
+// Two point tiles ("slots" A, B; P = 8 points each) are in flight: while the tensor pipe runs the MMAs of
+// one slot, the epilogue warps work on the other slot.  One CTA-wide barrier per step.
+//
+// Per tile the stages are  s = 0: layer 0 (K = 2, FFMA);  s = 1..L-1: hidden layer s (fwd MMA);  s = L:
+// output layer (MMA) + residuals + adjoint seeds;  s = L+1..2L-1: reverse of hidden layer l = 2L-s
+// (dgrad MMA -> adjoint of layer l-1, wgrad MMA accumulating dW_l in TMEM for the whole kernel).
+//
+// Every MMA operand is K-major, no swizzle (measured: MN-major tf32 needs the 32B-atom swizzle):
+//   weight image (A operand)       : rows j, 16-byte K chunks 128 B apart, 8-row bands 2560 B apart
+//   "R" image (B operand, fwd/dgrad): rows n = 4p+s, contraction over neurons; chunk stride padded to
+//                                     144 B so that the per-neuron scalar stores are conflict free
+//   "C" image (A / B of wgrad)      : rows = neuron, contraction over n; one 16-byte chunk = the 4 streams
+//                                     of a point (a single st.shared.v4 per thread and point)
+#include "nsf_internal.h"
+#include "nsf_tc.cuh"
+
+using namespace nsftc;
+
+namespace {
+
+constexpr int KP = 80;            // hidden width handled by this kernel
+constexpr int P = 8;              // points per tile slot
+constexpr int NCOL = 4 * P;       // MMA N of the forward / dgrad contractions
+constexpr int NW = 80;            // MMA N of the weight-gradient contraction (columns of dW_l)
+constexpr int MAXL = 6;           // (L-1)*80 + 2*32 <= 512 TMEM columns
+constexpr int NTHREADS = 288;
+
+constexpr uint32_t W_SBO = (KP / 4) * 128;      // 2560: 8-row band of a weight image
+constexpr uint32_t IMG = (KP / 8) * W_SBO;      // 25600: one weight image (hi or lo)
+constexpr uint32_t WBUF = 2 * IMG;              // hi | lo
+constexpr uint32_t R_LBO = 144, R_SBO = (KP / 4) * R_LBO;   // 2880
+constexpr uint32_t RB = (NCOL / 8) * R_SBO;     // 11520: one R image
+constexpr uint32_t C_SP = (KP / 8) * 128;       // 1280: point block of a C image
+constexpr uint32_t CB = P * C_SP;               // 10240: one C image
+constexpr uint32_t SLOT = 2 * RB + 4 * CB;      // 64000: R hi, R lo, ZC hi, ZC lo, AC hi, AC lo
+constexpr uint32_t OFF_SLOT = 2 * WBUF;         // 102400
+constexpr uint32_t OFF_MISC = OFF_SLOT + 2 * SLOT;   // 230400
+constexpr uint32_t MISC = 1536;
+constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;     // 231936 <= 232448
+
+struct UArgs {
+  NsfNetGeom g;
+  const float* pk;       // FFMA packed image: layer 0, biases, output layer rows
+  const uint8_t* wimg;   // (2L-1) weight images of WBUF bytes: WF_1..WF_L, WB_{L-1}..WB_1
+  const float* x; const float* y; long long n;
+  int train;             // 0: residuals only
+  const float* e_in; const float* vtm_in; float* vtm_out; const float* w;
+  float inv_Re, vis_t0, alpha_evm, cs1, cs2, k4, c_eq;
+  int has_evm;
+  float* resid_out; float* vis_t_out; float* ebar_out;
+  float* stash;          // [grid][2][L][P][KP][4]
+  float* scratch;        // gradient rows [grid][gs_row]
+  int n_pairs;
+};
+
+struct Misc {
+  uint64_t mbar[2];      // MMA completion per slot
+  uint64_t wbar[2];      // weight image landed per buffer
+  uint32_t tmem_base;
+  uint32_t pad[3];
+  float ov[2][P][16];    // outputs / output adjoints [slot][p][4*s + o]
+  float red[P][12];
+};
+static_assert(sizeof(Misc) <= MISC, "misc region too small");
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void st4(uint8_t* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void st1(uint8_t* p, float a) { *reinterpret_cast<float*>(p) = a; }
+
+// image index (0-based) used by MMA stage s (1..2L-1) of a tile
+__device__ __forceinline__ int img_of_stage(int s) { return s - 1; }
+
+// ---- issuer: all MMAs of stage s for one slot -------------------------------------------------
+__device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint32_t tmem, int s, int slot, int wbuf, bool zero_dw) {
+  const int L = a.g.L;
+  const uint32_t wa = smem_u32(smem) + (uint32_t)wbuf * WBUF;
+  const uint32_t sb = smem_u32(smem) + OFF_SLOT + (uint32_t)slot * SLOT;
+  const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
+  {  // forward (s <= L) or dgrad (s > L): D[128, 4P] = Wimg[128, 80] * R[4P, 80]^T
+    const uint32_t idesc = idesc_tf32(128, NCOL, 0, 0);
+    const uint32_t rh = sb, rl = sb + RB;
+#pragma unroll 1
+    for (int ks = 0; ks < KP / 8; ++ks) {
+      const uint64_t ah = smem_desc(wa + ks * 256, 128, W_SBO), al = smem_desc(wa + IMG + ks * 256, 128, W_SBO);
+      const uint64_t bh = smem_desc(rh + ks * 2 * R_LBO, R_LBO, R_SBO), bl = smem_desc(rl + ks * 2 * R_LBO, R_LBO, R_SBO);
+      mma_tf32(d_col, al, bh, idesc, ks > 0);
+      mma_tf32(d_col, ah, bl, idesc, 1);
+      mma_tf32(d_col, ah, bh, idesc, 1);
+    }
+  }
+  if (s > L) {  // wgrad: dW_l[128, 80] += ZC[128, 4P] * AC[80, 4P]^T
+    const int l = 2 * L - s;
+    const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
+    const uint32_t dw_col = tmem + (uint32_t)((l - 1) * NW);
+    const uint32_t zh = sb + 2 * RB, zl = zh + CB, ch = zl + CB, cl = ch + CB;
+#pragma unroll 1
+    for (int ks = 0; ks < NCOL / 8; ++ks) {
+      const uint32_t o = ks * 2 * C_SP;
+      const uint64_t ah = smem_desc(zh + o, C_SP, 128), al = smem_desc(zl + o, C_SP, 128);
+      const uint64_t bh = smem_desc(ch + o, C_SP, 128), bl = smem_desc(cl + o, C_SP, 128);
+      mma_tf32(dw_col, al, bh, idesc, !(zero_dw && ks == 0));
+      mma_tf32(dw_col, ah, bl, idesc, 1);
+      mma_tf32(dw_col, ah, bh, idesc, 1);
+    }
+  }
+}
+
+// ---- epilogue helpers ---------------------------------------------------------------------------
+struct Epi {
+  int j, h, q, lane;
+  bool active;           // j < KP
+  uint32_t lane_addr;    // TMEM lane field of this warp's quadrant
+  uint32_t r_off;        // byte offset of (n = 0, j) in an R image
+  uint32_t c_off;        // byte offset of (j, point 0) in a C image
+};
+
+// tanh jet of one point: z -> activations; returns t
+__device__ __forceinline__ void jet_fwd(const float z[4], float& t, float& ax, float& ay, float& al) {
+  t = tanhf(z[0]);
+  const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1;
+  ax = d1 * z[1]; ay = d1 * z[2];
+  al = fmaf(d2, fmaf(z[1], z[1], z[2] * z[2]), d1 * z[3]);
+}
+
+// write the 4 streams of point p (tile-local index) for neuron j into an R image pair
+__device__ __forceinline__ void store_R(uint8_t* rh, uint8_t* rl, const Epi& e, int p, const float v[4]) {
+  const uint32_t base = (uint32_t)(p >> 1) * R_SBO + (uint32_t)((p & 1) * 4) * 16 + e.r_off;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    float hi, lo;
+    split_tf32(v[s], hi, lo);
+    st1(rh + base + s * 16, hi);
+    st1(rl + base + s * 16, lo);
+  }
+}
+__device__ __forceinline__ void store_C(uint8_t* ch, uint8_t* cl, const Epi& e, int p, const float v[4]) {
+  float hi[4], lo[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) split_tf32(v[s], hi[s], lo[s]);
+  const uint32_t off = (uint32_t)p * C_SP + e.c_off;
+  st4(ch + off, hi[0], hi[1], hi[2], hi[3]);
+  st4(cl + off, lo[0], lo[1], lo[2], lo[3]);
+}
+
+// forward epilogue of layer l for this thread's 4 points: z (pre-activations incl. bias) -> R image (+ stash)
+__device__ __forceinline__ void epi_forward(const UArgs& a, uint8_t* slot_base, const Epi& e, float* stash_slot, int l,
+                                            float z[4][4]) {
+  uint8_t* rh = slot_base; uint8_t* rl = slot_base + RB;
+#pragma unroll
+  for (int pi = 0; pi < 4; ++pi) {
+    const int p = e.h * 4 + pi;
+    float t, v[4];
+    jet_fwd(z[pi], t, v[1], v[2], v[3]);
+    v[0] = t;
+    if (a.train) {
+      float4* sp = reinterpret_cast<float4*>(stash_slot + ((size_t)(l * P + p) * KP + e.j) * 4);
+      __stcs(sp, make_float4(t, z[pi][1], z[pi][2], z[pi][3]));
+    }
+    store_R(rh, rl, e, p, v);
+  }
+}
+
+// reverse epilogue of layer l: adjoints of the activations (ab) -> pre-activation adjoints; writes the R and C
+// images of zb and (l >= 1) the C image of a^{l-1}; returns zb for layer 0 handling
+__device__ __forceinline__ void epi_reverse(const UArgs& a, uint8_t* slot_base, const Epi& e, const float* stash_slot, int l,
+                                            const float ab[4][4], float zb[4][4], float act[4][4]) {
+  uint8_t* rh = slot_base; uint8_t* rl = rh + RB;
+  uint8_t* zh = rl + RB; uint8_t* zl = zh + CB; uint8_t* ch = zl + CB; uint8_t* cl = ch + CB;
+#pragma unroll
+  for (int pi = 0; pi < 4; ++pi) {
+    const int p = e.h * 4 + pi;
+    const float4 st = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)(l * P + p) * KP + e.j) * 4));
+    const float t = st.x, zx = st.y, zy = st.z, zl_ = st.w;
+    const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1, d3 = -2.f * d1 * fmaf(-3.f * t, t, 1.f);
+    const float a0 = ab[pi][0], ax = ab[pi][1], ay = ab[pi][2], al = ab[pi][3];
+    zb[pi][3] = al * d1;
+    zb[pi][1] = fmaf(ax, d1, 2.f * al * d2 * zx);
+    zb[pi][2] = fmaf(ay, d1, 2.f * al * d2 * zy);
+    zb[pi][0] = fmaf(a0, d1, fmaf(ax * d2, zx, fmaf(ay * d2, zy, al * fmaf(d3, fmaf(zx, zx, zy * zy), d2 * zl_))));
+    // the layer's own activations (for the output-layer weight gradient when l = L-1)
+    act[pi][0] = t; act[pi][1] = d1 * zx; act[pi][2] = d1 * zy; act[pi][3] = fmaf(d2, fmaf(zx, zx, zy * zy), d1 * zl_);
+    if (l >= 1) {
+      store_R(rh, rl, e, p, zb[pi]);
+      store_C(zh, zl, e, p, zb[pi]);
+      const float4 s1 = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)((l - 1) * P + p) * KP + e.j) * 4));
+      const float e1 = fmaf(-s1.x, s1.x, 1.f), e2 = -2.f * s1.x * e1;
+      float av[4];
+      av[0] = s1.x; av[1] = e1 * s1.y; av[2] = e1 * s1.z;
+      av[3] = fmaf(e2, fmaf(s1.y, s1.y, s1.z * s1.z), e1 * s1.w);
+      store_C(ch, cl, e, p, av);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Misc* misc = reinterpret_cast<Misc*>(smem + OFF_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const NsfNetGeom& g = a.g;
+  const int L = g.L;
+  const int nstage = a.train ? 2 * L : L + 1;       // stages per tile
+  const int nsteps = 2 * nstage;                    // steps per tile pair
+
+  if (warp == 0) tmem_alloc(&misc->tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&misc->mbar[0], 1); mbar_init(&misc->mbar[1], 1);
+    mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
+    mbar_fence_init();
+  }
+  // zero the operand slots once: padded rows / stale data must at least be finite-free of surprises
+  for (uint32_t i = tid * 16; i < 2 * SLOT; i += NTHREADS * 16) *reinterpret_cast<float4*>(smem + OFF_SLOT + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc->tmem_base;
+
+  const int my_pairs = ((int)blockIdx.x < a.n_pairs) ? (a.n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 8) {
+    // =========================== issuer warp ===========================
+    // lane 0 does the work; the whole warp walks the step loop so that every thread meets every barrier
+    const long long total_mma_stages = (long long)my_pairs * (nstage - 1);
+    long long loaded = 0;      // weight images requested so far (one per MMA stage, in stage order)
+    uint32_t wphase[2] = {0, 0};
+    auto load_next = [&]() {
+      if (loaded >= total_mma_stages) return;
+      const int b = (int)(loaded & 1);
+      const int img = (int)(loaded % (nstage - 1));
+      mbar_expect_tx(&misc->wbar[b], WBUF);
+      tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
+      ++loaded;
+    };
+    if (lane == 0) { load_next(); load_next(); }
+    long long mma_stage = 0;   // MMA stages fully issued (both slots) so far
+    uint32_t mphase[2] = {0, 0};
+    bool w_ready = false;
+    for (int pr = 0; pr < my_pairs; ++pr) {
+      for (int step = 0; step < nsteps; ++step) {
+        if (lane == 0) {
+          // (a) issue the MMAs whose operands were completed by the previous step's epilogue
+          if (step >= 1) {
+            const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
+            const int s = ps + 1;                                     // stage to issue for that slot
+            if (s < nstage) {
+              const int b = (int)(mma_stage & 1);
+              if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
+              issue_stage(a, smem, tmem, s, pslot, b, pr == 0 && pslot == 0);
+              mma_commit(&misc->mbar[pslot]);
+              if (pslot == 1) { ++mma_stage; w_ready = false; }
+            }
+          }
+          // (b) when slot B's MMAs of a stage have completed, its weight buffer is free: prefetch two stages ahead
+          const int slot = step & 1, s = step >> 1;
+          if (s >= 1) {
+            mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1;
+            if (slot == 1) load_next();
+          }
+        }
+        __syncwarp();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    Epi e;
+    e.lane = lane; e.q = warp & 3; e.h = warp >> 2;
+    e.j = e.q * 32 + lane;
+    e.active = e.j < KP;
+    e.lane_addr = (uint32_t)(e.q * 32) << 16;
+    e.r_off = (uint32_t)(e.j >> 2) * R_LBO + (uint32_t)(e.j & 3) * 4;
+    e.c_off = (uint32_t)(e.j >> 3) * 128 + (uint32_t)(e.j & 7) * 16;
+    const int jj = e.active ? e.j : 0;
+    const float* pk = a.pk;
+    const float w0x = __ldg(pk + g.pk_w0x() + jj), w0y = __ldg(pk + g.pk_w0y() + jj), b0 = __ldg(pk + g.pk_b0() + jj);
+    const float wl0 = __ldg(pk + g.pk_wl() + jj), wl1 = __ldg(pk + g.pk_wl() + g.HP + jj), wl2 = __ldg(pk + g.pk_wl() + 2 * g.HP + jj);
+    float* stash_cta = a.stash ? a.stash + (size_t)blockIdx.x * 2 * L * P * KP * 4 : nullptr;
+    float* grow = a.scratch ? a.scratch + (size_t)blockIdx.x * g.gs_row() : nullptr;
+    // per-thread gradient partials (this neuron, this half of the points)
+    float gw0x = 0.f, gw0y = 0.f, gwl[3] = {0.f, 0.f, 0.f};
+    float gb[MAXL];
+#pragma unroll
+    for (int i = 0; i < MAXL; ++i) gb[i] = 0.f;
+    float lossacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gbl[3] = {0.f, 0.f, 0.f};   // threads tid < P only
+    uint32_t mphase[2] = {0, 0};
+
+    for (int pr = 0; pr < my_pairs; ++pr) {
+      const long long pair = (long long)blockIdx.x + (long long)pr * gridDim.x;
+      for (int step = 0; step < nsteps; ++step) {
+        const int slot = step & 1, s = step >> 1;
+        const long long p0 = (pair * 2 + slot) * P;                       // first point of this slot's tile
+        const int nvalid = (int)((a.n - p0) < 0 ? 0 : ((a.n - p0) < P ? (a.n - p0) : P));
+        uint8_t* sb = smem + OFF_SLOT + (size_t)slot * SLOT;
+        float* stash_slot = stash_cta ? stash_cta + (size_t)slot * L * P * KP * 4 : nullptr;
+        const uint32_t d_addr = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + slot * NCOL + e.h * 16);
+        if (s >= 1) { mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1; tc_fence_after(); }
+
+        if (s == 0) {
+          // ---- layer 0 (K = 2) -------------------------------------------------------------
+          if (e.active) {
+            float z[4][4];
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) {
+              const int p = e.h * 4 + pi;
+              const float xv = p < nvalid ? __ldg(a.x + p0 + p) : 0.f, yv = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
+              z[pi][0] = fmaf(w0x, xv, fmaf(w0y, yv, b0)); z[pi][1] = w0x; z[pi][2] = w0y; z[pi][3] = 0.f;
+            }
+            epi_forward(a, sb, e, stash_slot, 0, z);
+          }
+        } else if (s < L) {
+          // ---- hidden layer s forward --------------------------------------------------------
+          float z[4][4];
+          tmem_ld16(d_addr, &z[0][0]);
+          tmem_ld_wait();
+          if (e.active) {
+            const float b = __ldg(pk + g.pk_b(s) + e.j);
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) z[pi][0] += b;
+            epi_forward(a, sb, e, stash_slot, s, z);
+          }
+        } else if (s == L) {
+          // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
+          float o[4][4];
+          tmem_ld16(d_addr, &o[0][0]);
+          tmem_ld_wait();
+          if (e.q == 0 && lane < 3) {
+            const float bo = __ldg(pk + g.pk_bl() + lane);
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) {
+              const int p = e.h * 4 + pi;
+              misc->ov[slot][p][0 * 4 + lane] = o[pi][0] + bo;
+              misc->ov[slot][p][1 * 4 + lane] = o[pi][1];
+              misc->ov[slot][p][2 * 4 + lane] = o[pi][2];
+              misc->ov[slot][p][3 * 4 + lane] = o[pi][3];
+            }
+          }
+          epi_bar();
+          if (tid < P) {
+            const int p = tid;
+            const bool ok = p < nvalid;
+            const long long gp = p0 + p;
+            float* ov = misc->ov[slot][p];
+            const float u = ov[0], v = ov[1];
+            const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
+            const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
+            const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
+            float ee = 0.f, vis = 0.f;
+            if (a.has_evm) {
+              ee = ok ? __ldg(a.e_in + gp) : 0.f;
+              vis = a.vis_t0;
+              if (a.vtm_in && ok) vis = fminf(a.vis_t0, __ldg(a.vtm_in + gp));
+            }
+            const float nu = a.inv_Re + vis;
+            const float eq1 = (u * ux + v * uy) + px - nu * ul;
+            const float eq2 = (u * vx + v * vy) + py - nu * vl;
+            const float eq3 = ux + vy;
+            const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
+            const float w = (a.w && ok) ? __ldg(a.w + gp) : 1.f;
+            if (ok) {
+              lossacc[0] += w * eq1 * eq1; lossacc[1] += w * eq2 * eq2; lossacc[2] += w * eq3 * eq3; lossacc[3] += w * eq4 * eq4;
+              lossacc[4] += vis; lossacc[5] += 1.f;
+              if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
+              if (a.vis_t_out) a.vis_t_out[gp] = vis;
+              if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
+            }
+            if (a.train) {
+              const float cw = ok ? a.c_eq * w : 0.f;
+              const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
+              const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
+              const float g3 = 2.f * cw * eq3;
+              const float g4 = a.k4 * cw * eq4;
+              ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
+              ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
+              ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
+              ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
+              gbl[0] += ov[0]; gbl[1] += ov[1]; gbl[2] += ov[2];
+              if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
+            }
+          }
+          if (a.train) {
+            epi_bar();
+            if (e.active) {
+              float ab[4][4], zb[4][4], act[4][4];
+#pragma unroll
+              for (int pi = 0; pi < 4; ++pi) {
+                const float* ov = misc->ov[slot][e.h * 4 + pi];
+#pragma unroll
+                for (int st = 0; st < 4; ++st) ab[pi][st] = fmaf(ov[st * 4 + 0], wl0, fmaf(ov[st * 4 + 1], wl1, ov[st * 4 + 2] * wl2));
+              }
+              epi_reverse(a, sb, e, stash_slot, L - 1, ab, zb, act);
+#pragma unroll
+              for (int pi = 0; pi < 4; ++pi) {
+                const float* ov = misc->ov[slot][e.h * 4 + pi];
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                  gwl[0] = fmaf(ov[st * 4 + 0], act[pi][st], gwl[0]);
+                  gwl[1] = fmaf(ov[st * 4 + 1], act[pi][st], gwl[1]);
+                  gwl[2] = fmaf(ov[st * 4 + 2], act[pi][st], gwl[2]);
+                }
+              }
+              {
+                float sb0 = 0.f;
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi) sb0 += zb[pi][0];
+#pragma unroll
+                for (int i = 0; i < MAXL; ++i) if (i == L - 1) gb[i] += sb0;
+              }
+            }
+          }
+        } else {
+          // ---- reverse: D holds the adjoint of layer l's activations, l = 2L - s - 1 ------------------
+          const int l = 2 * L - s - 1;
+          float ab[4][4];
+          tmem_ld16(d_addr, &ab[0][0]);
+          tmem_ld_wait();
+          if (e.active) {
+            float zb[4][4], act[4][4];
+            epi_reverse(a, sb, e, stash_slot, l, ab, zb, act);
+            float sb0 = 0.f;
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) sb0 += zb[pi][0];
+#pragma unroll
+            for (int i = 0; i < MAXL; ++i) if (i == l) gb[i] += sb0;
+            if (l == 0) {
+#pragma unroll
+              for (int pi = 0; pi < 4; ++pi) {
+                const int p = e.h * 4 + pi;
+                const float xv = p < nvalid ? __ldg(a.x + p0 + p) : 0.f, yv = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
+                gw0x += fmaf(zb[pi][0], xv, zb[pi][1]); gw0y += fmaf(zb[pi][0], yv, zb[pi][2]);
+              }
+            }
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+      }
+    }
+
+    // ---- CTA epilogue: gradients -> this CTA's row ---------------------------------------------
+    // (all MMAs have completed: every stage's completion barrier was waited on above)
+    tc_fence_after();
+    if (grow) {
+      float* redf = reinterpret_cast<float*>(smem + OFF_SLOT);   // operand slots are free now: [KP][16] partials of half 1
+      if (e.h == 1 && e.active) {
+        float* r = redf + e.j * 16;
+        r[0] = gw0x; r[1] = gw0y; r[2] = gwl[0]; r[3] = gwl[1]; r[4] = gwl[2];
+#pragma unroll
+        for (int i = 0; i < MAXL; ++i) r[5 + i] = gb[i];
+      }
+      if (tid < P) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) misc->red[tid][k] = lossacc[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) misc->red[tid][6 + k] = gbl[k];
+      }
+      epi_bar();
+      if (a.train && e.h == 0 && e.active) {
+        const float* r = redf + e.j * 16;
+        const int j = e.j;
+        grow[g.gs_w0x() + j] = gw0x + r[0];
+        grow[g.gs_w0y() + j] = gw0y + r[1];
+        grow[g.gs_b0() + j] = gb[0] + r[5];
+        grow[g.gs_wl() + j] = gwl[0] + r[2];
+        grow[g.gs_wl() + g.HP + j] = gwl[1] + r[3];
+        grow[g.gs_wl() + 2 * g.HP + j] = gwl[2] + r[4];
+        grow[g.gs_wl() + 3 * g.HP + j] = 0.f;
+#pragma unroll
+        for (int l = 1; l < MAXL; ++l)
+          if (l < L) grow[g.gs_b(l) + j] = gb[l] + r[5 + l];
+      }
+      if (a.train && e.h == 0) {
+        // dW_l accumulators: TMEM lane = j, columns (l-1)*80 + k
+        for (int l = 1; l < L; ++l) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < NW; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + e.lane_addr + (uint32_t)((l - 1) * NW + c0), v);
+            tmem_ld_wait();
+            if (e.active) {
+              float4* dst = reinterpret_cast<float4*>(grow + g.gs_w(l) + (size_t)e.j * g.HP + c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          }
+        }
+      }
+      if (tid < NSF_LOSS_SLOTS) {
+        float v = 0.f;
+        if (tid < 6) for (int p = 0; p < P; ++p) v += misc->red[p][tid];
+        grow[g.gs_loss() + tid] = v;
+      }
+      if (a.train && tid < 4) {
+        float v = 0.f;
+        if (tid < 3) for (int p = 0; p < P; ++p) v += misc->red[p][6 + tid];
+        grow[g.gs_bl() + tid] = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// weight images: thread per (image, j, k)
+__global__ void nsf_umma_pack_kernel(NsfNetGeom g, const float* __restrict__ flat, uint8_t* __restrict__ wimg) {
+  const int L = g.L, H = g.H;
+  const int n_img = 2 * L - 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_img * KP * KP) return;
+  const int img = (int)(idx / (KP * KP)), r = (int)(idx % (KP * KP)) / KP, c = (int)(idx % KP);   // row r (M index), contraction c
+  float v = 0.f;
+  if (img < L - 1) {                 // WF_l, l = img + 1: (j = r, k = c) = W_l[j][k]
+    const int l = img + 1, fo = 3 * H + (l - 1) * (H * H + H);
+    if (r < H && c < H) v = flat[fo + r * H + c];
+  } else if (img == L - 1) {         // output layer rows o < n_out
+    const int fo = 3 * H + (L - 1) * (H * H + H);
+    if (r < g.n_out && c < H) v = flat[fo + r * H + c];
+  } else {                           // WB_l, l = 2L - 1 - img: (m = k_in = r, c = j_out) = W_l[c][r]
+    const int l = 2 * L - 1 - img, fo = 3 * H + (l - 1) * (H * H + H);
+    if (r < H && c < H) v = flat[fo + c * H + r];
+  }
+  float hi, lo;
+  split_tf32(v, hi, lo);
+  const size_t off = (size_t)img * WBUF + (size_t)(r >> 3) * W_SBO + (size_t)(c >> 2) * 128 + (size_t)(r & 7) * 16 + (size_t)(c & 3) * 4;
+  *reinterpret_cast<float*>(wimg + off) = hi;
+  *reinterpret_cast<float*>(wimg + off + IMG) = lo;
+}
+
+struct UmmaState {
+  uint8_t* wimg = nullptr;
+  float* stash = nullptr;
+  int grid = 0;
+};
+
+}  // namespace
+
+int nsf_umma_supported(const NsfNetGeom& g) { return g.H == KP && g.n_out == 3 && g.L >= 2 && g.L <= MAXL; }
+
+int nsf_umma_init(NsfCtx* ctx) {
+  if (ctx->umma) return NSF_OK;
+  if (!nsf_umma_supported(ctx->main.g)) { nsf_set_error("tcgen05 path covers hidden = 80, 2..6 hidden layers"); return NSF_E_SHAPE; }
+  UmmaState* s = new UmmaState();
+  const NsfNetGeom& g = ctx->main.g;
+  s->grid = ctx->sms;
+  if (s->grid > ctx->main.rows) s->grid = ctx->main.rows;
+  NSF_CUDA_OK(cudaMalloc((void**)&s->wimg, (size_t)(2 * g.L - 1) * WBUF));
+  NSF_CUDA_OK(cudaMalloc((void**)&s->stash, (size_t)s->grid * 2 * g.L * P * KP * 4 * sizeof(float)));
+  NSF_CUDA_OK(cudaFuncSetAttribute(nsf_umma_jet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  ctx->ws_bytes += (long long)(2 * g.L - 1) * WBUF + (long long)s->grid * 2 * g.L * P * KP * 16;
+  ctx->umma = s;
+  return NSF_OK;
+}
+
+void nsf_umma_free(NsfCtx* ctx) {
+  UmmaState* s = (UmmaState*)ctx->umma;
+  if (!s) return;
+  cudaFree(s->wimg); cudaFree(s->stash);
+  delete s;
+  ctx->umma = nullptr;
+}
+
+// Collocation jet step / residuals on the tcgen05 path.  `k` carries the same fields the FFMA launch uses.
+// Returns the grid (rows written) through *grid_out.
+int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches) {
+  UmmaState* s = (UmmaState*)ctx->umma;
+  const NsfNetGeom& g = ctx->main.g;
+  const long long tot = (long long)(2 * g.L - 1) * KP * KP;
+  nsf_umma_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, flat_params, s->wimg);
+  NSF_CUDA_OK(cudaGetLastError());
+  ++*launches;
+  UArgs a;
+  a.g = g; a.pk = k.pk; a.wimg = s->wimg; a.x = k.x; a.y = k.y; a.n = k.n;
+  a.train = k.mode == NSF_MODE_JET_STEP ? 1 : 0;
+  a.e_in = k.e_in; a.vtm_in = k.vtm_in; a.vtm_out = k.vtm_out; a.w = k.w;
+  a.inv_Re = k.inv_Re; a.vis_t0 = k.vis_t0; a.alpha_evm = k.alpha_evm; a.cs1 = k.cs1; a.cs2 = k.cs2; a.k4 = k.k4; a.c_eq = k.c_eq;
+  a.has_evm = k.has_evm;
+  a.resid_out = k.resid_out; a.vis_t_out = k.vis_t_out; a.ebar_out = k.ebar_out;
+  a.stash = a.train ? s->stash : nullptr;
+  a.scratch = a.train ? k.scratch : nullptr;
+  a.n_pairs = (int)((k.n + 2 * P - 1) / (2 * P));
+  int grid = a.n_pairs < s->grid ? a.n_pairs : s->grid;
+  if (grid <= 0) { *grid_out = 0; return NSF_OK; }
+  nsf_umma_jet_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  NSF_CUDA_OK(cudaGetLastError());
+  ++*launches;
+  *grid_out = grid;
+  return NSF_OK;
+}

@@ -40,7 +40,7 @@ def test_step_matches_oracle(gu, L, H, n, nb, has_evm):
     phys = J.Physics(Re=1000., alpha_b=10., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
     r = J.step(pm, md, phys, x, y, xb, yb, ub, vb, evm_flat=pe if has_evm else None, evm_desc=ed if has_evm else None, w=w,
                vis_t_minus=vtm if has_evm else None)
-    abi = gu.Abi((2, 3, L, H), (2, 1, 4, 40) if has_evm else None)
+    abi = gu.Abi((2, 3, L, H), (2, 1, 4, 40) if has_evm else None, path=1)
     cp = _capi.physics(1000., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
     o = abi.step(pm, cp, x, y, blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)], params_evm=pe if has_evm else None, w=w,
                  vtm_in=vtm if has_evm else None)
@@ -62,7 +62,7 @@ def test_golden_ev_lag(gu, golden_dir):
     g = np.load(os.path.join(golden_dir, "ev_re2000_lag.npz"))
     xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
     nb, n = xb.size, g["xf"].size
-    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40))
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40), path=1)
     vtm = g["vis_t_minus_init"]
     for k in range(int(g["steps"])):
         cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
@@ -192,3 +192,57 @@ def test_full_size_properties(gu):
                evm_flat=pe, evm_desc=ed, vis_t_minus=vtm[:m].cpu().numpy())
     assert gu.rel(o["grad_main"], r.grad_main) < TOL
     assert abs(sum(o["loss_parts"][:3]) / m - sum(r.loss_eq[:3])) < TOL * sum(r.loss_eq[:3])
+
+
+# ---- tcgen05 (3xTF32) path: same bar as the FP32 path -------------------------------------------------
+@pytest.mark.parametrize("L,n,nb", [(6, 1333, 132), (2, 16, 8), (3, 5, 3), (6, 100000, 2052), (4, 777, 40)])
+@pytest.mark.parametrize("has_evm", [False, True])
+def test_umma_step_matches_oracle(gu, L, n, nb, has_evm):
+    H = 80
+    rng = np.random.default_rng(L * 100 + n)
+    md, ed = J.NetDesc(2, 3, L, H), J.NetDesc(2, 1, 4, 40)
+    pm, pe = J.init_params(md, 1) * 1.5, J.init_params(ed, 2)
+    x, y = rng.random(n).astype(np.float32), rng.random(n).astype(np.float32)
+    xb, yb, ub, vb = [rng.random(nb).astype(np.float32) for _ in range(4)]
+    w = (0.5 + rng.random(n)).astype(np.float32)
+    vtm = (rng.random(n) * 0.02).astype(np.float32)
+    cs = 1.3 if has_evm else 1.0
+    phys = J.Physics(Re=1000., alpha_b=10., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
+    r = J.step(pm, md, phys, x, y, xb, yb, ub, vb, evm_flat=pe if has_evm else None, evm_desc=ed if has_evm else None, w=w,
+               vis_t_minus=vtm if has_evm else None)
+    abi = gu.Abi((2, 3, L, H), (2, 1, 4, 40) if has_evm else None, path=2)
+    cp = _capi.physics(1000., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
+    o = abi.step(pm, cp, x, y, blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)], params_evm=pe if has_evm else None, w=w,
+                 vtm_in=vtm if has_evm else None)
+    assert o["info"]["path"] == 2
+    errs = dict(grad=gu.rel(o["grad_main"], r.grad_main), eq=[gu.rel(o["resid"][k], r.eq[k]) for k in range(4 if has_evm else 3)])
+    print("umma", L, n, has_evm, errs)
+    assert errs["grad"] < TOL
+    for k in range(4 if has_evm else 3):
+        assert errs["eq"][k] < TOL
+        assert abs(o["loss_parts"][k] / n - r.loss_eq[k]) < TOL * r.loss_eq[k]
+    assert o["loss_parts"][5] == n
+    assert abs((o["loss_parts"][6] + o["loss_parts"][7]) / nb - r.loss_b) < TOL * r.loss_b
+    if has_evm:
+        assert gu.rel(o["grad_evm"], r.grad_evm) < TOL
+        assert gu.rel(o["vtm_out"], r.vis_t_minus_next) < TOL
+    # determinism
+    o2 = abi.step(pm, cp, x, y, blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)], params_evm=pe if has_evm else None, w=w,
+                  vtm_in=vtm if has_evm else None)
+    assert np.array_equal(o["grad_main"], o2["grad_main"])
+
+
+def test_umma_golden_ev_lag(gu, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ev_re2000_lag.npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb, n = xb.size, g["xf"].size
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40), path=2)
+    vtm = g["vis_t_minus_init"]
+    for k in range(int(g["steps"])):
+        cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
+        o = abi.step(g[f"params_main_{k}"], cp, g["xf"], g["yf"], blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)],
+                     params_evm=g[f"params_evm_{k}"], vtm_in=vtm)
+        assert gu.rel(o["grad_main"], g[f"grad_main_{k}"]) < TOL
+        for i in range(4):
+            assert gu.rel(o["resid"][i], g[f"eq{i+1}_{k}"]) < TOL
+        vtm = o["vtm_out"]
