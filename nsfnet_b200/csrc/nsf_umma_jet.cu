@@ -35,6 +35,7 @@ constexpr int NCOL = 4 * P;       // MMA N of the forward / dgrad contractions
 constexpr int NW = 80;            // MMA N of the weight-gradient contraction (columns of dW_l)
 constexpr int MAXL = 6;           // (L-1)*80 + 2*32 <= 512 TMEM columns
 constexpr int NTHREADS = 288;
+constexpr int FLUSH = 32;         // tile pairs between flushes of the TMEM weight-gradient accumulators
 
 constexpr uint32_t W_SBO = (KP / 4) * 128;      // 2560: 8-row band of a weight image
 constexpr uint32_t IMG = (KP / 8) * W_SBO;      // 25600: one weight image (hi or lo)
@@ -91,37 +92,45 @@ __device__ __forceinline__ void st1(uint8_t* p, float a) { *reinterpret_cast<flo
 // image index (0-based) used by MMA stage s (1..2L-1) of a tile
 __device__ __forceinline__ int img_of_stage(int s) { return s - 1; }
 
-// ---- issuer: all MMAs of stage s for one slot -------------------------------------------------
-__device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint32_t tmem, int s, int slot, int wbuf, bool zero_dw) {
+// ---- issuer: all MMAs of stage s for one slot (executed by the whole issuer warp, see mma_tf32_elect) ----
+__device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint32_t tmem, int s, int slot, int wbuf, bool zero_dw,
+                                            uint32_t leader) {
   const int L = a.g.L;
   const uint32_t wa = smem_u32(smem) + (uint32_t)wbuf * WBUF;
   const uint32_t sb = smem_u32(smem) + OFF_SLOT + (uint32_t)slot * SLOT;
   const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
   {  // forward (s <= L) or dgrad (s > L): D[128, 4P] = Wimg[128, 80] * R[4P, 80]^T
+    // The tensor core truncates when it adds into the fp32 accumulator (measured: -2e-8 relative per MMA for
+    // same-sign sums).  Issue the 2^-11-sized correction products first, while the accumulator is still small,
+    // and the hi*hi products last: 10 full-magnitude accumulations per layer instead of 30.
     const uint32_t idesc = idesc_tf32(128, NCOL, 0, 0);
-    const uint32_t rh = sb, rl = sb + RB;
-#pragma unroll 1
+    const uint64_t ah0 = smem_desc(wa, 128, W_SBO), al0 = smem_desc(wa + IMG, 128, W_SBO);
+    const uint64_t bh0 = smem_desc(sb, R_LBO, R_SBO), bl0 = smem_desc(sb + RB, R_LBO, R_SBO);
+#pragma unroll
     for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint64_t ah = smem_desc(wa + ks * 256, 128, W_SBO), al = smem_desc(wa + IMG + ks * 256, 128, W_SBO);
-      const uint64_t bh = smem_desc(rh + ks * 2 * R_LBO, R_LBO, R_SBO), bl = smem_desc(rl + ks * 2 * R_LBO, R_LBO, R_SBO);
-      mma_tf32(d_col, al, bh, idesc, ks > 0);
-      mma_tf32(d_col, ah, bl, idesc, 1);
-      mma_tf32(d_col, ah, bh, idesc, 1);
+      const uint64_t da = (uint64_t)(ks * (256 >> 4)), db = (uint64_t)(ks * ((2 * R_LBO) >> 4));
+      mma_tf32_elect(d_col, al0 + da, bh0 + db, idesc, ks > 0, leader);
+      mma_tf32_elect(d_col, ah0 + da, bl0 + db, idesc, 1, leader);
+    }
+#pragma unroll
+    for (int ks = 0; ks < KP / 8; ++ks) {
+      const uint64_t da = (uint64_t)(ks * (256 >> 4)), db = (uint64_t)(ks * ((2 * R_LBO) >> 4));
+      mma_tf32_elect(d_col, ah0 + da, bh0 + db, idesc, 1, leader);
     }
   }
   if (s > L) {  // wgrad: dW_l[128, 80] += ZC[128, 4P] * AC[80, 4P]^T
     const int l = 2 * L - s;
     const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
     const uint32_t dw_col = tmem + (uint32_t)((l - 1) * NW);
-    const uint32_t zh = sb + 2 * RB, zl = zh + CB, ch = zl + CB, cl = ch + CB;
-#pragma unroll 1
+    const uint32_t zh = sb + 2 * RB;
+    const uint64_t ah0 = smem_desc(zh, C_SP, 128), al0 = smem_desc(zh + CB, C_SP, 128);
+    const uint64_t bh0 = smem_desc(zh + 2 * CB, C_SP, 128), bl0 = smem_desc(zh + 3 * CB, C_SP, 128);
+#pragma unroll
     for (int ks = 0; ks < NCOL / 8; ++ks) {
-      const uint32_t o = ks * 2 * C_SP;
-      const uint64_t ah = smem_desc(zh + o, C_SP, 128), al = smem_desc(zl + o, C_SP, 128);
-      const uint64_t bh = smem_desc(ch + o, C_SP, 128), bl = smem_desc(cl + o, C_SP, 128);
-      mma_tf32(dw_col, al, bh, idesc, !(zero_dw && ks == 0));
-      mma_tf32(dw_col, ah, bl, idesc, 1);
-      mma_tf32(dw_col, ah, bh, idesc, 1);
+      const uint64_t d = (uint64_t)(ks * ((2 * C_SP) >> 4));
+      mma_tf32_elect(dw_col, al0 + d, bh0 + d, idesc, !(zero_dw && ks == 0), leader);
+      mma_tf32_elect(dw_col, ah0 + d, bl0 + d, idesc, 1, leader);
+      mma_tf32_elect(dw_col, ah0 + d, bh0 + d, idesc, 1, leader);
     }
   }
 }
@@ -213,6 +222,28 @@ __device__ __forceinline__ void epi_reverse(const UArgs& a, uint8_t* slot_base, 
   }
 }
 
+// dW_l accumulators (TMEM lane = j, columns (l-1)*80 + k) -> this CTA's gradient row.  Bounds the number of
+// truncating accumulations per value (see issue_stage) independently of the point count.
+__device__ __forceinline__ void flush_dw(const NsfNetGeom& g, float* grow, uint32_t tmem, const Epi& e, bool first) {
+  for (int l = 1 + e.h; l < g.L; l += 2) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < NW; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + e.lane_addr + (uint32_t)((l - 1) * NW + c0), v);
+      tmem_ld_wait();
+      if (e.active) {
+        float4* dst = reinterpret_cast<float4*>(grow + g.gs_w(l) + (size_t)e.j * g.HP + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (!first) { const float4 p = dst[i]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          dst[i] = o;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + OFF_MISC);
@@ -240,7 +271,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 
   if (warp == 8) {
     // =========================== issuer warp ===========================
-    // lane 0 does the work; the whole warp walks the step loop so that every thread meets every barrier
+    // The whole warp walks the loop convergently with warp-uniform state; one elected lane issues the TMA
+    // copies, the MMAs and the commits.
+    const uint32_t leader = elect_one();
     const long long total_mma_stages = (long long)my_pairs * (nstage - 1);
     long long loaded = 0;      // weight images requested so far (one per MMA stage, in stage order)
     uint32_t wphase[2] = {0, 0};
@@ -248,30 +281,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       if (loaded >= total_mma_stages) return;
       const int b = (int)(loaded & 1);
       const int img = (int)(loaded % (nstage - 1));
-      mbar_expect_tx(&misc->wbar[b], WBUF);
-      tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
+      if (leader) {
+        mbar_expect_tx(&misc->wbar[b], WBUF);
+        tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
+      }
       ++loaded;
     };
-    if (lane == 0) { load_next(); load_next(); }
+    load_next(); load_next();
     long long mma_stage = 0;   // MMA stages fully issued (both slots) so far
     uint32_t mphase[2] = {0, 0};
     bool w_ready = false;
     for (int pr = 0; pr < my_pairs; ++pr) {
       for (int step = 0; step < nsteps; ++step) {
-        if (lane == 0) {
-          // (a) issue the MMAs whose operands were completed by the previous step's epilogue
-          if (step >= 1) {
-            const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
-            const int s = ps + 1;                                     // stage to issue for that slot
-            if (s < nstage) {
-              const int b = (int)(mma_stage & 1);
-              if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
-              issue_stage(a, smem, tmem, s, pslot, b, pr == 0 && pslot == 0);
-              mma_commit(&misc->mbar[pslot]);
-              if (pslot == 1) { ++mma_stage; w_ready = false; }
-            }
+        // (a) issue the MMAs whose operands were completed by the previous step's epilogue
+        if (step >= 1) {
+          const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
+          const int s = ps + 1;                                     // stage to issue for that slot
+          if (s < nstage) {
+            const int b = (int)(mma_stage & 1);
+            if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
+            issue_stage(a, smem, tmem, s, pslot, b, (pr % FLUSH) == 0 && pslot == 0, leader);
+            mma_commit_elect(&misc->mbar[pslot], leader);
+            if (pslot == 1) { ++mma_stage; w_ready = false; }
           }
-          // (b) when slot B's MMAs of a stage have completed, its weight buffer is free: prefetch two stages ahead
+        }
+        // (b) when slot B's MMAs of a stage have completed, its weight buffer is free: prefetch two stages ahead
+        {
           const int slot = step & 1, s = step >> 1;
           if (s >= 1) {
             mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1;
@@ -458,6 +493,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         tc_fence_before();
         __syncthreads();
       }
+      if (a.train && grow && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
+        // every MMA of this pair has completed (its barriers were waited on above); the next pair's first
+        // weight-gradient MMA is issued several CTA barriers from here
+        tc_fence_after();
+        flush_dw(g, grow, tmem, e, pr < FLUSH);
+        tc_fence_before();
+      }
     }
 
     // ---- CTA epilogue: gradients -> this CTA's row ---------------------------------------------
@@ -491,22 +533,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 #pragma unroll
         for (int l = 1; l < MAXL; ++l)
           if (l < L) grow[g.gs_b(l) + j] = gb[l] + r[5 + l];
-      }
-      if (a.train && e.h == 0) {
-        // dW_l accumulators: TMEM lane = j, columns (l-1)*80 + k
-        for (int l = 1; l < L; ++l) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < NW; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + e.lane_addr + (uint32_t)((l - 1) * NW + c0), v);
-            tmem_ld_wait();
-            if (e.active) {
-              float4* dst = reinterpret_cast<float4*>(grow + g.gs_w(l) + (size_t)e.j * g.HP + c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-          }
-        }
       }
       if (tid < NSF_LOSS_SLOTS) {
         float v = 0.f;

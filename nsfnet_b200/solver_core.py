@@ -39,6 +39,15 @@ def _dev_f32(a, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
 
 
+def shard_bounds(total: int, rank: int, world_size: int):
+    """Contiguous block split of the reference (ev :144-147, :165-168): N // W points per rank, the last
+    rank takes the remainder."""
+    per = total // world_size
+    s = rank * per
+    e = s + per if rank < world_size - 1 else total
+    return s, e
+
+
 class _StepFn(torch.autograd.Function):
     """loss = nsf_step(...); backward hands out the gradient the kernel already produced."""
 
@@ -145,10 +154,7 @@ class SolverBase:
 
     # ---- setters (ev :142-262, NSFnet :82-110) -------------------------------------------------
     def _shard(self, total):
-        per = total // self.world_size
-        s = self.rank * per
-        e = s + per if self.rank < self.world_size - 1 else total
-        return s, e
+        return shard_bounds(total, self.rank, self.world_size)
 
     def set_boundary_data(self, X=None, time=False):
         total = np.asarray(X[0]).shape[0]
