@@ -28,6 +28,7 @@ static inline float nsf_ldg(const float* p) { return *p; }
 static inline float nsf_tanh(float x) { return std::tanh(x); }
 static inline float nsf_fma(float a, float b, float c) { return std::fma(a, b, c); }
 #else
+#include "nsf_math.cuh"
 #define NSF_DEV __device__ __forceinline__
 typedef float4 nsf_f4;
 NSF_DEV nsf_f4 nsf_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -36,7 +37,7 @@ NSF_DEV nsf_f4 nsf_ldcs4(const float* p) { return __ldcs(reinterpret_cast<const 
 NSF_DEV void nsf_st4(float* p, nsf_f4 v) { *reinterpret_cast<float4*>(p) = v; }
 NSF_DEV void nsf_stcs4(float* p, nsf_f4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 NSF_DEV float nsf_ldg(const float* p) { return __ldg(p); }
-NSF_DEV float nsf_tanh(float x) { return tanhf(x); }
+NSF_DEV float nsf_tanh(float x) { return nsf_tanh_fast(x); }
 NSF_DEV float nsf_fma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 

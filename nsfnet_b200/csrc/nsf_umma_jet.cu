@@ -6,9 +6,11 @@
 // An epilogue thread owns one neuron of a quarter of the tile's points: it reads its 4 stream values of a
 // point with ONE tcgen05.ld, applies the tanh jet on FFMA / MUFU and writes the next layer's operands.
 //
-// One CTA per SM (persistent), 9 warps:
-//   warps 0-7 : epilogue (warp w -> TMEM lane quadrant w & 3, points 4*(w >> 2) .. +3 of the tile)
-//   warp  8   : issuer (one lane): TMA bulk loads of the weight images, tcgen05.mma, tcgen05.commit
+// One CTA per SM (persistent), 15 warps.  A warp may only touch the TMEM lane quadrant (warp id & 3), and the 80
+// neurons live in quadrants 0-2, so:
+//   warps 4*sub + q, q = 0..2, sub = 0..3 : epilogue (quadrant q, points 2*sub, 2*sub+1 of the tile) -- 12 warps
+//   warp 3                                : issuer (elected lane): TMA bulk loads of the weight images, tcgen05.mma, commit
+//   warps 7, 11                           : spare (quadrant 3 holds only padding rows)
 // Two point tiles ("slots" A, B; P = 8 points each) are in flight: while the tensor pipe runs the MMAs of
 // one slot, the epilogue warps work on the other slot.  One CTA-wide barrier per step.
 //
@@ -24,6 +26,7 @@
 //                                     of a point (a single st.shared.v4 per thread and point)
 #include "nsf_internal.h"
 #include "nsf_tc.cuh"
+#include "nsf_math.cuh"
 
 using namespace nsftc;
 
@@ -34,7 +37,12 @@ constexpr int P = 8;              // points per tile slot
 constexpr int NCOL = 4 * P;       // MMA N of the forward / dgrad contractions
 constexpr int NW = 80;            // MMA N of the weight-gradient contraction (columns of dW_l)
 constexpr int MAXL = 6;           // (L-1)*80 + 2*32 <= 512 TMEM columns
-constexpr int NTHREADS = 288;
+constexpr int PPT = 2;            // points per epilogue thread and stage
+constexpr int NSUB = P / PPT;     // epilogue warps per TMEM lane quadrant
+constexpr int NWARPS = 4 * NSUB - 1;   // warps 4*sub + q, q = 0..2 epilogue; warp 3 issuer; warps 7, 11 idle
+constexpr int NTHREADS = NWARPS * 32;  // 480
+constexpr int NEPI = 3 * NSUB * 32;    // 384 epilogue threads
+constexpr int ISSUER_WARP = 3;
 constexpr int FLUSH = 32;         // tile pairs between flushes of the TMEM weight-gradient accumulators
 
 constexpr uint32_t W_SBO = (KP / 4) * 128;      // 2560: 8-row band of a weight image
@@ -82,7 +90,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
+// step barrier: epilogue warps + issuer warp (the two spare warps of quadrant 3 do not take part)
+__device__ __forceinline__ void step_bar() { asm volatile("bar.sync 2, %0;" ::"n"(NEPI + 32) : "memory"); }
 
 __device__ __forceinline__ void st4(uint8_t* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
@@ -137,7 +147,7 @@ __device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint3
 
 // ---- epilogue helpers ---------------------------------------------------------------------------
 struct Epi {
-  int j, h, q, lane;
+  int j, sub, q, lane;
   bool active;           // j < KP
   uint32_t lane_addr;    // TMEM lane field of this warp's quadrant
   uint32_t r_off;        // byte offset of (n = 0, j) in an R image
@@ -146,7 +156,7 @@ struct Epi {
 
 // tanh jet of one point: z -> activations; returns t
 __device__ __forceinline__ void jet_fwd(const float z[4], float& t, float& ax, float& ay, float& al) {
-  t = tanhf(z[0]);
+  t = nsf_tanh_fast(z[0]);
   const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1;
   ax = d1 * z[1]; ay = d1 * z[2];
   al = fmaf(d2, fmaf(z[1], z[1], z[2] * z[2]), d1 * z[3]);
@@ -174,11 +184,11 @@ __device__ __forceinline__ void store_C(uint8_t* ch, uint8_t* cl, const Epi& e, 
 
 // forward epilogue of layer l for this thread's 4 points: z (pre-activations incl. bias) -> R image (+ stash)
 __device__ __forceinline__ void epi_forward(const UArgs& a, uint8_t* slot_base, const Epi& e, float* stash_slot, int l,
-                                            float z[4][4]) {
+                                            float z[PPT][4]) {
   uint8_t* rh = slot_base; uint8_t* rl = slot_base + RB;
 #pragma unroll
-  for (int pi = 0; pi < 4; ++pi) {
-    const int p = e.h * 4 + pi;
+  for (int pi = 0; pi < PPT; ++pi) {
+    const int p = e.sub * PPT + pi;
     float t, v[4];
     jet_fwd(z[pi], t, v[1], v[2], v[3]);
     v[0] = t;
@@ -193,13 +203,13 @@ __device__ __forceinline__ void epi_forward(const UArgs& a, uint8_t* slot_base, 
 // reverse epilogue of layer l: adjoints of the activations (ab) -> pre-activation adjoints; writes the R and C
 // images of zb and (l >= 1) the C image of a^{l-1}; returns zb for layer 0 handling
 __device__ __forceinline__ void epi_reverse(const UArgs& a, uint8_t* slot_base, const Epi& e, const float* stash_slot, int l,
-                                            const float ab[4][4], float zb[4][4], float act[4][4]) {
+                                            const float ab[PPT][4], float zb[PPT][4], float act[PPT][4], const float4* st_l, const float4* st_lm1) {
   uint8_t* rh = slot_base; uint8_t* rl = rh + RB;
   uint8_t* zh = rl + RB; uint8_t* zl = zh + CB; uint8_t* ch = zl + CB; uint8_t* cl = ch + CB;
 #pragma unroll
-  for (int pi = 0; pi < 4; ++pi) {
-    const int p = e.h * 4 + pi;
-    const float4 st = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)(l * P + p) * KP + e.j) * 4));
+  for (int pi = 0; pi < PPT; ++pi) {
+    const int p = e.sub * PPT + pi;
+    const float4 st = st_l[pi];
     const float t = st.x, zx = st.y, zy = st.z, zl_ = st.w;
     const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1, d3 = -2.f * d1 * fmaf(-3.f * t, t, 1.f);
     const float a0 = ab[pi][0], ax = ab[pi][1], ay = ab[pi][2], al = ab[pi][3];
@@ -212,7 +222,7 @@ __device__ __forceinline__ void epi_reverse(const UArgs& a, uint8_t* slot_base, 
     if (l >= 1) {
       store_R(rh, rl, e, p, zb[pi]);
       store_C(zh, zl, e, p, zb[pi]);
-      const float4 s1 = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)((l - 1) * P + p) * KP + e.j) * 4));
+      const float4 s1 = st_lm1[pi];
       const float e1 = fmaf(-s1.x, s1.x, 1.f), e2 = -2.f * s1.x * e1;
       float av[4];
       av[0] = s1.x; av[1] = e1 * s1.y; av[2] = e1 * s1.z;
@@ -225,7 +235,7 @@ __device__ __forceinline__ void epi_reverse(const UArgs& a, uint8_t* slot_base, 
 // dW_l accumulators (TMEM lane = j, columns (l-1)*80 + k) -> this CTA's gradient row.  Bounds the number of
 // truncating accumulations per value (see issue_stage) independently of the point count.
 __device__ __forceinline__ void flush_dw(const NsfNetGeom& g, float* grow, uint32_t tmem, const Epi& e, bool first) {
-  for (int l = 1 + e.h; l < g.L; l += 2) {
+  for (int l = 1 + e.sub; l < g.L; l += NSUB) {
 #pragma unroll 1
     for (int c0 = 0; c0 < NW; c0 += 16) {
       float v[16];
@@ -269,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 
   const int my_pairs = ((int)blockIdx.x < a.n_pairs) ? (a.n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == 8) {
+  if (warp == ISSUER_WARP) {
     // =========================== issuer warp ===========================
     // The whole warp walks the loop convergently with warp-uniform state; one elected lane issues the TMA
     // copies, the MMAs and the commits.
@@ -315,14 +325,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         }
         __syncwarp();
         tc_fence_before();
-        __syncthreads();
+        step_bar();
         tc_fence_after();
       }
     }
-  } else {
+  } else if ((warp & 3) != 3) {
     // =========================== epilogue warps ===========================
     Epi e;
-    e.lane = lane; e.q = warp & 3; e.h = warp >> 2;
+    e.lane = lane; e.q = warp & 3; e.sub = warp >> 2;
     e.j = e.q * 32 + lane;
     e.active = e.j < KP;
     e.lane_addr = (uint32_t)(e.q * 32) << 16;
@@ -334,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     const float wl0 = __ldg(pk + g.pk_wl() + jj), wl1 = __ldg(pk + g.pk_wl() + g.HP + jj), wl2 = __ldg(pk + g.pk_wl() + 2 * g.HP + jj);
     float* stash_cta = a.stash ? a.stash + (size_t)blockIdx.x * 2 * L * P * KP * 4 : nullptr;
     float* grow = a.scratch ? a.scratch + (size_t)blockIdx.x * g.gs_row() : nullptr;
-    // per-thread gradient partials (this neuron, this half of the points)
+    // per-thread gradient partials (this neuron, this thread's share of the points)
     float gw0x = 0.f, gw0y = 0.f, gwl[3] = {0.f, 0.f, 0.f};
     float gb[MAXL];
 #pragma unroll
@@ -350,16 +360,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         const int nvalid = (int)((a.n - p0) < 0 ? 0 : ((a.n - p0) < P ? (a.n - p0) : P));
         uint8_t* sb = smem + OFF_SLOT + (size_t)slot * SLOT;
         float* stash_slot = stash_cta ? stash_cta + (size_t)slot * L * P * KP * 4 : nullptr;
-        const uint32_t d_addr = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + slot * NCOL + e.h * 16);
+        const uint32_t d_addr = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + slot * NCOL + e.sub * (4 * PPT));
+        // reverse stages: fetch the stashed pre-activations (L2) BEFORE waiting for the MMAs of this stage
+        const int lrev = (s >= L) ? 2 * L - s - 1 : -1;                    // layer whose tanh is differentiated (s = L: L-1)
+        float4 st_l[PPT], st_lm1[PPT];
+        if (a.train && lrev >= 0 && e.active) {
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            const int p = e.sub * PPT + pi;
+            st_l[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)(lrev * P + p) * KP + e.j) * 4));
+            if (lrev >= 1) st_lm1[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)((lrev - 1) * P + p) * KP + e.j) * 4));
+          }
+        }
         if (s >= 1) { mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1; tc_fence_after(); }
 
         if (s == 0) {
           // ---- layer 0 (K = 2) -------------------------------------------------------------
           if (e.active) {
-            float z[4][4];
+            float z[PPT][4];
 #pragma unroll
-            for (int pi = 0; pi < 4; ++pi) {
-              const int p = e.h * 4 + pi;
+            for (int pi = 0; pi < PPT; ++pi) {
+              const int p = e.sub * PPT + pi;
               const float xv = p < nvalid ? __ldg(a.x + p0 + p) : 0.f, yv = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
               z[pi][0] = fmaf(w0x, xv, fmaf(w0y, yv, b0)); z[pi][1] = w0x; z[pi][2] = w0y; z[pi][3] = 0.f;
             }
@@ -367,25 +388,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           }
         } else if (s < L) {
           // ---- hidden layer s forward --------------------------------------------------------
-          float z[4][4];
-          tmem_ld16(d_addr, &z[0][0]);
+          float z[PPT][4];
+          tmem_ld8(d_addr, &z[0][0]);
           tmem_ld_wait();
           if (e.active) {
             const float b = __ldg(pk + g.pk_b(s) + e.j);
 #pragma unroll
-            for (int pi = 0; pi < 4; ++pi) z[pi][0] += b;
+            for (int pi = 0; pi < PPT; ++pi) z[pi][0] += b;
             epi_forward(a, sb, e, stash_slot, s, z);
           }
         } else if (s == L) {
           // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
-          float o[4][4];
-          tmem_ld16(d_addr, &o[0][0]);
+          float o[PPT][4];
+          tmem_ld8(d_addr, &o[0][0]);
           tmem_ld_wait();
           if (e.q == 0 && lane < 3) {
             const float bo = __ldg(pk + g.pk_bl() + lane);
 #pragma unroll
-            for (int pi = 0; pi < 4; ++pi) {
-              const int p = e.h * 4 + pi;
+            for (int pi = 0; pi < PPT; ++pi) {
+              const int p = e.sub * PPT + pi;
               misc->ov[slot][p][0 * 4 + lane] = o[pi][0] + bo;
               misc->ov[slot][p][1 * 4 + lane] = o[pi][1];
               misc->ov[slot][p][2 * 4 + lane] = o[pi][2];
@@ -438,51 +459,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           if (a.train) {
             epi_bar();
             if (e.active) {
-              float ab[4][4], zb[4][4], act[4][4];
+              float ab[PPT][4], zb[PPT][4], act[PPT][4];
 #pragma unroll
-              for (int pi = 0; pi < 4; ++pi) {
-                const float* ov = misc->ov[slot][e.h * 4 + pi];
+              for (int pi = 0; pi < PPT; ++pi) {
+                const float* ov = misc->ov[slot][e.sub * PPT + pi];
 #pragma unroll
                 for (int st = 0; st < 4; ++st) ab[pi][st] = fmaf(ov[st * 4 + 0], wl0, fmaf(ov[st * 4 + 1], wl1, ov[st * 4 + 2] * wl2));
               }
-              epi_reverse(a, sb, e, stash_slot, L - 1, ab, zb, act);
+              epi_reverse(a, sb, e, stash_slot, L - 1, ab, zb, act, st_l, st_lm1);
+              float sb0 = 0.f;
 #pragma unroll
-              for (int pi = 0; pi < 4; ++pi) {
-                const float* ov = misc->ov[slot][e.h * 4 + pi];
+              for (int pi = 0; pi < PPT; ++pi) {
+                const float* ov = misc->ov[slot][e.sub * PPT + pi];
 #pragma unroll
                 for (int st = 0; st < 4; ++st) {
                   gwl[0] = fmaf(ov[st * 4 + 0], act[pi][st], gwl[0]);
                   gwl[1] = fmaf(ov[st * 4 + 1], act[pi][st], gwl[1]);
                   gwl[2] = fmaf(ov[st * 4 + 2], act[pi][st], gwl[2]);
                 }
+                sb0 += zb[pi][0];
               }
-              {
-                float sb0 = 0.f;
 #pragma unroll
-                for (int pi = 0; pi < 4; ++pi) sb0 += zb[pi][0];
-#pragma unroll
-                for (int i = 0; i < MAXL; ++i) if (i == L - 1) gb[i] += sb0;
-              }
+              for (int i = 0; i < MAXL; ++i) if (i == L - 1) gb[i] += sb0;
             }
           }
         } else {
           // ---- reverse: D holds the adjoint of layer l's activations, l = 2L - s - 1 ------------------
-          const int l = 2 * L - s - 1;
-          float ab[4][4];
-          tmem_ld16(d_addr, &ab[0][0]);
+          const int l = lrev;
+          float ab[PPT][4];
+          tmem_ld8(d_addr, &ab[0][0]);
           tmem_ld_wait();
           if (e.active) {
-            float zb[4][4], act[4][4];
-            epi_reverse(a, sb, e, stash_slot, l, ab, zb, act);
+            float zb[PPT][4], act[PPT][4];
+            epi_reverse(a, sb, e, stash_slot, l, ab, zb, act, st_l, st_lm1);
             float sb0 = 0.f;
 #pragma unroll
-            for (int pi = 0; pi < 4; ++pi) sb0 += zb[pi][0];
+            for (int pi = 0; pi < PPT; ++pi) sb0 += zb[pi][0];
 #pragma unroll
             for (int i = 0; i < MAXL; ++i) if (i == l) gb[i] += sb0;
             if (l == 0) {
 #pragma unroll
-              for (int pi = 0; pi < 4; ++pi) {
-                const int p = e.h * 4 + pi;
+              for (int pi = 0; pi < PPT; ++pi) {
+                const int p = e.sub * PPT + pi;
                 const float xv = p < nvalid ? __ldg(a.x + p0 + p) : 0.f, yv = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
                 gw0x += fmaf(zb[pi][0], xv, zb[pi][1]); gw0y += fmaf(zb[pi][0], yv, zb[pi][2]);
               }
@@ -491,7 +509,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        step_bar();
       }
       if (a.train && grow && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
         // every MMA of this pair has completed (its barriers were waited on above); the next pair's first
@@ -502,13 +520,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       }
     }
 
-    // ---- CTA epilogue: gradients -> this CTA's row ---------------------------------------------
-    // (all MMAs have completed: every stage's completion barrier was waited on above)
-    tc_fence_after();
+    // ---- CTA epilogue: thread-local gradient partials and loss sums -> this CTA's row -------------
     if (grow) {
-      float* redf = reinterpret_cast<float*>(smem + OFF_SLOT);   // operand slots are free now: [KP][16] partials of half 1
-      if (e.h == 1 && e.active) {
-        float* r = redf + e.j * 16;
+      float* redf = reinterpret_cast<float*>(smem + OFF_SLOT);   // operand slots are free now: [NSUB-1][KP][16]
+      if (e.sub >= 1 && e.active) {
+        float* r = redf + ((e.sub - 1) * KP + e.j) * 16;
         r[0] = gw0x; r[1] = gw0y; r[2] = gwl[0]; r[3] = gwl[1]; r[4] = gwl[2];
 #pragma unroll
         for (int i = 0; i < MAXL; ++i) r[5 + i] = gb[i];
@@ -520,8 +536,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         for (int k = 0; k < 3; ++k) misc->red[tid][6 + k] = gbl[k];
       }
       epi_bar();
-      if (a.train && e.h == 0 && e.active) {
-        const float* r = redf + e.j * 16;
+      if (a.train && e.sub == 0 && e.active) {
+        float r[5 + MAXL];
+#pragma unroll
+        for (int i = 0; i < 5 + MAXL; ++i) {
+          r[i] = 0.f;
+#pragma unroll
+          for (int q = 0; q < NSUB - 1; ++q) r[i] += redf[(q * KP + e.j) * 16 + i];
+        }
         const int j = e.j;
         grow[g.gs_w0x() + j] = gw0x + r[0];
         grow[g.gs_w0y() + j] = gw0y + r[1];
