@@ -116,6 +116,12 @@ int nsf_get_info(NsfCtx* ctx, int64_t info[4]);
 int nsf_set_timing(NsfCtx* ctx, int enable);
 int nsf_last_kernel_ms(NsfCtx* ctx, float* ms);
 
+/* Diagnostics of the tcgen05 kernel: out == NULL switches per-warp cycle counters on for the following launches;
+ * out != NULL (double[256]) synchronises the device and returns the counters of the last launch averaged over CTAs
+ * (layout documented at nsf_umma_stage_cycles in csrc/nsf_umma_jet.cu).  Adds clock reads to the kernel: not for
+ * timed runs. */
+int nsf_get_stage_cycles(NsfCtx* ctx, double* out);
+
 /* One `fwd_computing_loss_2d()` + `loss.backward()`:
  *   ev-NSFnet/pinn_solver.py:372-428 + :468-469 (DDP all-reduce excluded), i.e.
  *   neural_net_u on the blocks (:280-288), neural_net_equations on the collocation points

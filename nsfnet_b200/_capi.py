@@ -20,7 +20,7 @@ NSF_MAX_BLOCKS = 2
 NSF_LOSS_SLOTS = 16
 
 EXPORTS = ["nsf_abi_version", "nsf_last_error", "nsf_create", "nsf_destroy", "nsf_set_path", "nsf_get_info",
-           "nsf_set_timing", "nsf_last_kernel_ms",
+           "nsf_set_timing", "nsf_last_kernel_ms", "nsf_get_stage_cycles",
            "nsf_step", "nsf_residuals", "nsf_forward", "nsf_adam", "nsf_selftest_umma"]
 
 
@@ -64,6 +64,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nsf_set_timing.argtypes = [vp, C.c_int]
     lib.nsf_last_kernel_ms.restype = C.c_int
     lib.nsf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.nsf_get_stage_cycles.restype = C.c_int
+    lib.nsf_get_stage_cycles.argtypes = [vp, C.POINTER(C.c_double)]
     lib.nsf_step.restype = C.c_int
     lib.nsf_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(NsfDataBlock), i32, C.POINTER(NsfPhysics),
                              vp, vp, vp, vp, vp, vp, vp]
@@ -143,6 +145,14 @@ class Context:
         ms = C.c_float()
         check(self.lib, self.lib.nsf_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def stage_cycles(self, read: bool = True):
+        if not read:
+            check(self.lib, self.lib.nsf_get_stage_cycles(self.h, None))
+            return None
+        arr = (C.c_double * 256)()
+        check(self.lib, self.lib.nsf_get_stage_cycles(self.h, arr))
+        return [list(arr[w * 16:(w + 1) * 16]) for w in range(16)]
 
     def step(self, params_main, params_evm, x, y, w, vtm_in, vtm_out, n_f, blocks, phys, grad_main, grad_evm,
              loss_parts, residuals_out=None, e_out=None, vis_t_out=None, stream=None):

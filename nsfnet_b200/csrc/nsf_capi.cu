@@ -144,6 +144,16 @@ extern "C" int nsf_get_info(NsfCtx* ctx, int64_t info[4]) {
   return NSF_OK;
 }
 
+extern "C" int nsf_get_stage_cycles(NsfCtx* ctx, double* out) {
+  if (!ctx) { nsf_set_error("nsf_get_stage_cycles: null context"); return NSF_E_ARG; }
+#ifdef NSF_EMU
+  (void)out; nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE;
+#else
+  if (!nsf_umma_supported(ctx->main.g)) { nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not cover this net"); return NSF_E_SHAPE; }
+  return nsf_umma_stage_cycles(ctx, out);
+#endif
+}
+
 // the collocation jet launch (step or residuals) on whichever kernel family is selected
 static int launch_jet(NsfCtx* ctx, NsfKernelArgs& a, const float* flat_main, int* grid, nsf_stream_t st) {
 #ifndef NSF_EMU

@@ -84,6 +84,7 @@ int nsf_adam_launch(float* params, const float* grad, float* m, float* v, long l
 int nsf_umma_supported(const NsfNetGeom& g);
 int nsf_umma_init(NsfCtx* ctx);
 void nsf_umma_free(NsfCtx* ctx);
+int nsf_umma_stage_cycles(NsfCtx* ctx, double* out);
 int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 
 // flat parameter i of the packed image (host + device)

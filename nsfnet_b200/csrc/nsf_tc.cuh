@@ -98,6 +98,23 @@ __device__ __forceinline__ void mma_tf32_elect(uint32_t d_tmem, uint64_t adesc, 
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// same, descriptors given as 32-bit halves: the high halves (LBO / SBO / version) are compile-time constants and
+// only the 14-bit start-address field of the low half changes between MMAs -> one 32-bit add per operand
+__device__ __forceinline__ void mma_tf32_elect2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
+
 __device__ __forceinline__ void mma_commit_elect(uint64_t* bar, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -147,6 +164,14 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
   lo = tf32_rna(x - hi);
+}
+
+// Cheap split for the per-point operands of the jet kernel: hi = x rounded to tf32 by the integer trick (no
+// Inf/NaN handling -- activations and adjoints are finite), lo = x - hi exactly; the tensor core ignores the low
+// 13 bits of lo.  |error| <= 2^-21 |x|, 3 instructions instead of ~11 for two cvt.rna.tf32 (which sm_100 emulates).
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
 
 }  // namespace nsftc

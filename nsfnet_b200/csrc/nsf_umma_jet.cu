@@ -71,6 +71,7 @@ struct UArgs {
   float* stash;          // [grid][2][L][P][KP][4]
   float* scratch;        // gradient rows [grid][gs_row]
   int n_pairs;
+  long long* dbg;        // optional [grid][16 warps][16] cycle counters (nsf_get_stage_cycles)
 };
 
 struct Misc {
@@ -114,18 +115,19 @@ __device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint3
     // same-sign sums).  Issue the 2^-11-sized correction products first, while the accumulator is still small,
     // and the hi*hi products last: 10 full-magnitude accumulations per layer instead of 30.
     const uint32_t idesc = idesc_tf32(128, NCOL, 0, 0);
-    const uint64_t ah0 = smem_desc(wa, 128, W_SBO), al0 = smem_desc(wa + IMG, 128, W_SBO);
-    const uint64_t bh0 = smem_desc(sb, R_LBO, R_SBO), bl0 = smem_desc(sb + RB, R_LBO, R_SBO);
+    constexpr uint32_t AHI = desc_hi(W_SBO), BHI = desc_hi(R_SBO);
+    const uint32_t ah0 = desc_lo(wa, 128), al0 = desc_lo(wa + IMG, 128);
+    const uint32_t bh0 = desc_lo(sb, R_LBO), bl0 = desc_lo(sb + RB, R_LBO);
 #pragma unroll
     for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint64_t da = (uint64_t)(ks * (256 >> 4)), db = (uint64_t)(ks * ((2 * R_LBO) >> 4));
-      mma_tf32_elect(d_col, al0 + da, bh0 + db, idesc, ks > 0, leader);
-      mma_tf32_elect(d_col, ah0 + da, bl0 + db, idesc, 1, leader);
+      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_LBO) >> 4);
+      mma_tf32_elect2(d_col, al0 + da, AHI, bh0 + db, BHI, idesc, ks > 0, leader);
+      mma_tf32_elect2(d_col, ah0 + da, AHI, bl0 + db, BHI, idesc, 1, leader);
     }
 #pragma unroll
     for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint64_t da = (uint64_t)(ks * (256 >> 4)), db = (uint64_t)(ks * ((2 * R_LBO) >> 4));
-      mma_tf32_elect(d_col, ah0 + da, bh0 + db, idesc, 1, leader);
+      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_LBO) >> 4);
+      mma_tf32_elect2(d_col, ah0 + da, AHI, bh0 + db, BHI, idesc, 1, leader);
     }
   }
   if (s > L) {  // wgrad: dW_l[128, 80] += ZC[128, 4P] * AC[80, 4P]^T
@@ -133,14 +135,15 @@ __device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint3
     const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
     const uint32_t dw_col = tmem + (uint32_t)((l - 1) * NW);
     const uint32_t zh = sb + 2 * RB;
-    const uint64_t ah0 = smem_desc(zh, C_SP, 128), al0 = smem_desc(zh + CB, C_SP, 128);
-    const uint64_t bh0 = smem_desc(zh + 2 * CB, C_SP, 128), bl0 = smem_desc(zh + 3 * CB, C_SP, 128);
+    constexpr uint32_t CHI = desc_hi(128);
+    const uint32_t ah0 = desc_lo(zh, C_SP), al0 = desc_lo(zh + CB, C_SP);
+    const uint32_t bh0 = desc_lo(zh + 2 * CB, C_SP), bl0 = desc_lo(zh + 3 * CB, C_SP);
 #pragma unroll
     for (int ks = 0; ks < NCOL / 8; ++ks) {
-      const uint64_t d = (uint64_t)(ks * ((2 * C_SP) >> 4));
-      mma_tf32_elect(dw_col, al0 + d, bh0 + d, idesc, !(zero_dw && ks == 0), leader);
-      mma_tf32_elect(dw_col, ah0 + d, bl0 + d, idesc, 1, leader);
-      mma_tf32_elect(dw_col, ah0 + d, bh0 + d, idesc, 1, leader);
+      const uint32_t d = ks * ((2 * C_SP) >> 4);
+      mma_tf32_elect2(dw_col, al0 + d, CHI, bh0 + d, CHI, idesc, !(zero_dw && ks == 0), leader);
+      mma_tf32_elect2(dw_col, ah0 + d, CHI, bl0 + d, CHI, idesc, 1, leader);
+      mma_tf32_elect2(dw_col, ah0 + d, CHI, bh0 + d, CHI, idesc, 1, leader);
     }
   }
 }
@@ -152,6 +155,9 @@ struct Epi {
   uint32_t lane_addr;    // TMEM lane field of this warp's quadrant
   uint32_t r_off;        // byte offset of (n = 0, j) in an R image
   uint32_t c_off;        // byte offset of (j, point 0) in a C image
+  uint32_t r_base[PPT];  // byte offset of (n = 4p, j) in an R image for this thread's points
+  uint32_t c_base[PPT];  // byte offset of (j, point p) in a C image
+  uint32_t s_base[PPT];  // float offset of (layer 0, point p, neuron j) in a stash slot
 };
 
 // tanh jet of one point: z -> activations; returns t
@@ -163,71 +169,62 @@ __device__ __forceinline__ void jet_fwd(const float z[4], float& t, float& ax, f
 }
 
 // write the 4 streams of point p (tile-local index) for neuron j into an R image pair
-__device__ __forceinline__ void store_R(uint8_t* rh, uint8_t* rl, const Epi& e, int p, const float v[4]) {
-  const uint32_t base = (uint32_t)(p >> 1) * R_SBO + (uint32_t)((p & 1) * 4) * 16 + e.r_off;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    float hi, lo;
-    split_tf32(v[s], hi, lo);
-    st1(rh + base + s * 16, hi);
-    st1(rl + base + s * 16, lo);
-  }
-}
-__device__ __forceinline__ void store_C(uint8_t* ch, uint8_t* cl, const Epi& e, int p, const float v[4]) {
+__device__ __forceinline__ void store_RC(uint8_t* rh, uint8_t* zh, const Epi& e, int pi, const float v[4], bool do_r, bool do_c) {
   float hi[4], lo[4];
 #pragma unroll
-  for (int s = 0; s < 4; ++s) split_tf32(v[s], hi[s], lo[s]);
-  const uint32_t off = (uint32_t)p * C_SP + e.c_off;
-  st4(ch + off, hi[0], hi[1], hi[2], hi[3]);
-  st4(cl + off, lo[0], lo[1], lo[2], lo[3]);
+  for (int s = 0; s < 4; ++s) split_tf32_fast(v[s], hi[s], lo[s]);
+  if (do_r) {
+    const uint32_t base = e.r_base[pi];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { st1(rh + base + s * 16, hi[s]); st1(rh + RB + base + s * 16, lo[s]); }
+  }
+  if (do_c) {
+    const uint32_t off = e.c_base[pi];
+    st4(zh + off, hi[0], hi[1], hi[2], hi[3]);
+    st4(zh + CB + off, lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
-// forward epilogue of layer l for this thread's 4 points: z (pre-activations incl. bias) -> R image (+ stash)
+// forward epilogue of layer l for this thread's points: z (pre-activations incl. bias) -> R image (+ stash)
 __device__ __forceinline__ void epi_forward(const UArgs& a, uint8_t* slot_base, const Epi& e, float* stash_slot, int l,
                                             float z[PPT][4]) {
-  uint8_t* rh = slot_base; uint8_t* rl = slot_base + RB;
 #pragma unroll
   for (int pi = 0; pi < PPT; ++pi) {
-    const int p = e.sub * PPT + pi;
     float t, v[4];
     jet_fwd(z[pi], t, v[1], v[2], v[3]);
     v[0] = t;
-    if (a.train) {
-      float4* sp = reinterpret_cast<float4*>(stash_slot + ((size_t)(l * P + p) * KP + e.j) * 4);
-      __stcs(sp, make_float4(t, z[pi][1], z[pi][2], z[pi][3]));
-    }
-    store_R(rh, rl, e, p, v);
+    if (a.train) __stcs(reinterpret_cast<float4*>(stash_slot + (size_t)l * (P * KP * 4) + e.s_base[pi]), make_float4(t, z[pi][1], z[pi][2], z[pi][3]));
+    store_RC(slot_base, nullptr, e, pi, v, true, false);
   }
 }
 
 // reverse epilogue of layer l: adjoints of the activations (ab) -> pre-activation adjoints; writes the R and C
-// images of zb and (l >= 1) the C image of a^{l-1}; returns zb for layer 0 handling
-__device__ __forceinline__ void epi_reverse(const UArgs& a, uint8_t* slot_base, const Epi& e, const float* stash_slot, int l,
-                                            const float ab[PPT][4], float zb[PPT][4], float act[PPT][4], const float4* st_l, const float4* st_lm1) {
-  uint8_t* rh = slot_base; uint8_t* rl = rh + RB;
-  uint8_t* zh = rl + RB; uint8_t* zl = zh + CB; uint8_t* ch = zl + CB; uint8_t* cl = ch + CB;
+// images of zb and (l >= 1) the C image of a^{l-1}; st_l / st_lm1 are the stashed (t, zx, zy, z_lap) of layers l, l-1
+__device__ __forceinline__ void epi_reverse(uint8_t* slot_base, const Epi& e, int l, const float ab[PPT][4], float zb[PPT][4],
+                                            float act[PPT][4], const float4* st_l, const float4* st_lm1) {
+  uint8_t* zh = slot_base + 2 * RB;
+  uint8_t* ch = zh + 2 * CB;
 #pragma unroll
   for (int pi = 0; pi < PPT; ++pi) {
-    const int p = e.sub * PPT + pi;
     const float4 st = st_l[pi];
     const float t = st.x, zx = st.y, zy = st.z, zl_ = st.w;
     const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1, d3 = -2.f * d1 * fmaf(-3.f * t, t, 1.f);
     const float a0 = ab[pi][0], ax = ab[pi][1], ay = ab[pi][2], al = ab[pi][3];
+    const float q = fmaf(zx, zx, zy * zy);
     zb[pi][3] = al * d1;
     zb[pi][1] = fmaf(ax, d1, 2.f * al * d2 * zx);
     zb[pi][2] = fmaf(ay, d1, 2.f * al * d2 * zy);
-    zb[pi][0] = fmaf(a0, d1, fmaf(ax * d2, zx, fmaf(ay * d2, zy, al * fmaf(d3, fmaf(zx, zx, zy * zy), d2 * zl_))));
+    zb[pi][0] = fmaf(a0, d1, fmaf(ax * d2, zx, fmaf(ay * d2, zy, al * fmaf(d3, q, d2 * zl_))));
     // the layer's own activations (for the output-layer weight gradient when l = L-1)
-    act[pi][0] = t; act[pi][1] = d1 * zx; act[pi][2] = d1 * zy; act[pi][3] = fmaf(d2, fmaf(zx, zx, zy * zy), d1 * zl_);
+    act[pi][0] = t; act[pi][1] = d1 * zx; act[pi][2] = d1 * zy; act[pi][3] = fmaf(d2, q, d1 * zl_);
     if (l >= 1) {
-      store_R(rh, rl, e, p, zb[pi]);
-      store_C(zh, zl, e, p, zb[pi]);
+      store_RC(slot_base, zh, e, pi, zb[pi], true, true);
       const float4 s1 = st_lm1[pi];
       const float e1 = fmaf(-s1.x, s1.x, 1.f), e2 = -2.f * s1.x * e1;
       float av[4];
       av[0] = s1.x; av[1] = e1 * s1.y; av[2] = e1 * s1.z;
       av[3] = fmaf(e2, fmaf(s1.y, s1.y, s1.z * s1.z), e1 * s1.w);
-      store_C(ch, cl, e, p, av);
+      store_RC(nullptr, ch, e, pi, av, false, true);
     }
   }
 }
@@ -301,8 +298,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     long long mma_stage = 0;   // MMA stages fully issued (both slots) so far
     uint32_t mphase[2] = {0, 0};
     bool w_ready = false;
+    long long icnt[5] = {0, 0, 0, 0, 0};   // weight wait, issue, MMA wait, barrier, steps
     for (int pr = 0; pr < my_pairs; ++pr) {
       for (int step = 0; step < nsteps; ++step) {
+        long long t0 = 0, t1 = 0;
+        if (a.dbg) t0 = clock64();
         // (a) issue the MMAs whose operands were completed by the previous step's epilogue
         if (step >= 1) {
           const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
@@ -310,11 +310,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           if (s < nstage) {
             const int b = (int)(mma_stage & 1);
             if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
+            if (a.dbg) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
             issue_stage(a, smem, tmem, s, pslot, b, (pr % FLUSH) == 0 && pslot == 0, leader);
             mma_commit_elect(&misc->mbar[pslot], leader);
             if (pslot == 1) { ++mma_stage; w_ready = false; }
           }
         }
+        if (a.dbg) { t1 = clock64(); icnt[1] += t1 - t0; t0 = t1; }
         // (b) when slot B's MMAs of a stage have completed, its weight buffer is free: prefetch two stages ahead
         {
           const int slot = step & 1, s = step >> 1;
@@ -324,10 +326,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           }
         }
         __syncwarp();
-        tc_fence_before();
+        if (a.dbg) { t1 = clock64(); icnt[2] += t1 - t0; t0 = t1; }
         step_bar();
         tc_fence_after();
+        if (a.dbg) { t1 = clock64(); icnt[3] += t1 - t0; icnt[4] += 1; }
       }
+    }
+    if (a.dbg && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = icnt[i];
     }
   } else if ((warp & 3) != 3) {
     // =========================== epilogue warps ===========================
@@ -338,6 +345,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     e.lane_addr = (uint32_t)(e.q * 32) << 16;
     e.r_off = (uint32_t)(e.j >> 2) * R_LBO + (uint32_t)(e.j & 3) * 4;
     e.c_off = (uint32_t)(e.j >> 3) * 128 + (uint32_t)(e.j & 7) * 16;
+#pragma unroll
+    for (int pi = 0; pi < PPT; ++pi) {
+      const int p = e.sub * PPT + pi;
+      e.r_base[pi] = (uint32_t)(p >> 1) * R_SBO + (uint32_t)((p & 1) * 4) * 16 + e.r_off;
+      e.c_base[pi] = (uint32_t)p * C_SP + e.c_off;
+      e.s_base[pi] = (uint32_t)((p * KP + (e.active ? e.j : 0)) * 4);
+    }
     const int jj = e.active ? e.j : 0;
     const float* pk = a.pk;
     const float w0x = __ldg(pk + g.pk_w0x() + jj), w0y = __ldg(pk + g.pk_w0y() + jj), b0 = __ldg(pk + g.pk_b0() + jj);
@@ -351,6 +365,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     for (int i = 0; i < MAXL; ++i) gb[i] = 0.f;
     float lossacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gbl[3] = {0.f, 0.f, 0.f};   // threads tid < P only
     uint32_t mphase[2] = {0, 0};
+    long long tcnt[10];      // [fwd | rev] x {MMA wait, work, fence, barrier, steps}
+#pragma unroll
+    for (int i = 0; i < 10; ++i) tcnt[i] = 0;
 
     for (int pr = 0; pr < my_pairs; ++pr) {
       const long long pair = (long long)blockIdx.x + (long long)pr * gridDim.x;
@@ -367,12 +384,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         if (a.train && lrev >= 0 && e.active) {
 #pragma unroll
           for (int pi = 0; pi < PPT; ++pi) {
-            const int p = e.sub * PPT + pi;
-            st_l[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)(lrev * P + p) * KP + e.j) * 4));
-            if (lrev >= 1) st_lm1[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + ((size_t)((lrev - 1) * P + p) * KP + e.j) * 4));
+            st_l[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + (size_t)lrev * (P * KP * 4) + e.s_base[pi]));
+            if (lrev >= 1) st_lm1[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + (size_t)(lrev - 1) * (P * KP * 4) + e.s_base[pi]));
           }
         }
+        // operands that come from L2 (the L1 is ~1 KB next to 227 KB of shared memory): issue the loads before the wait
+        float bias_s = 0.f, xv[PPT], yv[PPT];
+        if (e.active && s >= 1 && s < L) bias_s = __ldg(pk + g.pk_b(s) + e.j);
+        if (s == 0 || s == 2 * L - 1) {
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            const int p = e.sub * PPT + pi;
+            xv[pi] = p < nvalid ? __ldg(a.x + p0 + p) : 0.f;
+            yv[pi] = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
+          }
+        }
+        const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
+        long long t0 = 0, t1 = 0;
+        if (a.dbg) t0 = clock64();
         if (s >= 1) { mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1; tc_fence_after(); }
+        if (a.dbg) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
 
         if (s == 0) {
           // ---- layer 0 (K = 2) -------------------------------------------------------------
@@ -380,9 +411,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             float z[PPT][4];
 #pragma unroll
             for (int pi = 0; pi < PPT; ++pi) {
-              const int p = e.sub * PPT + pi;
-              const float xv = p < nvalid ? __ldg(a.x + p0 + p) : 0.f, yv = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
-              z[pi][0] = fmaf(w0x, xv, fmaf(w0y, yv, b0)); z[pi][1] = w0x; z[pi][2] = w0y; z[pi][3] = 0.f;
+              z[pi][0] = fmaf(w0x, xv[pi], fmaf(w0y, yv[pi], b0)); z[pi][1] = w0x; z[pi][2] = w0y; z[pi][3] = 0.f;
             }
             epi_forward(a, sb, e, stash_slot, 0, z);
           }
@@ -392,9 +421,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           tmem_ld8(d_addr, &z[0][0]);
           tmem_ld_wait();
           if (e.active) {
-            const float b = __ldg(pk + g.pk_b(s) + e.j);
 #pragma unroll
-            for (int pi = 0; pi < PPT; ++pi) z[pi][0] += b;
+            for (int pi = 0; pi < PPT; ++pi) z[pi][0] += bias_s;
             epi_forward(a, sb, e, stash_slot, s, z);
           }
         } else if (s == L) {
@@ -466,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 #pragma unroll
                 for (int st = 0; st < 4; ++st) ab[pi][st] = fmaf(ov[st * 4 + 0], wl0, fmaf(ov[st * 4 + 1], wl1, ov[st * 4 + 2] * wl2));
               }
-              epi_reverse(a, sb, e, stash_slot, L - 1, ab, zb, act, st_l, st_lm1);
+              epi_reverse(sb, e, L - 1, ab, zb, act, st_l, st_lm1);
               float sb0 = 0.f;
 #pragma unroll
               for (int pi = 0; pi < PPT; ++pi) {
@@ -491,7 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           tmem_ld_wait();
           if (e.active) {
             float zb[PPT][4], act[PPT][4];
-            epi_reverse(a, sb, e, stash_slot, l, ab, zb, act, st_l, st_lm1);
+            epi_reverse(sb, e, l, ab, zb, act, st_l, st_lm1);
             float sb0 = 0.f;
 #pragma unroll
             for (int pi = 0; pi < PPT; ++pi) sb0 += zb[pi][0];
@@ -500,16 +528,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             if (l == 0) {
 #pragma unroll
               for (int pi = 0; pi < PPT; ++pi) {
-                const int p = e.sub * PPT + pi;
-                const float xv = p < nvalid ? __ldg(a.x + p0 + p) : 0.f, yv = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
-                gw0x += fmaf(zb[pi][0], xv, zb[pi][1]); gw0y += fmaf(zb[pi][0], yv, zb[pi][2]);
+                gw0x += fmaf(zb[pi][0], xv[pi], zb[pi][1]); gw0y += fmaf(zb[pi][0], yv[pi], zb[pi][2]);
               }
             }
           }
         }
+        if (a.dbg) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
         fence_async_smem();
         tc_fence_before();
+        if (a.dbg) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; }
         step_bar();
+        if (a.dbg) { t0 = clock64(); tcnt[cls + 3] += t0 - t1; tcnt[cls + 4] += 1; }
       }
       if (a.train && grow && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
         // every MMA of this pair has completed (its barriers were waited on above); the next pair's first
@@ -520,6 +549,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       }
     }
 
+    if (a.dbg && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = tcnt[i];
+    }
     // ---- CTA epilogue: thread-local gradient partials and loss sums -> this CTA's row -------------
     if (grow) {
       float* redf = reinterpret_cast<float*>(smem + OFF_SLOT);   // operand slots are free now: [NSUB-1][KP][16]
@@ -601,10 +634,15 @@ __global__ void nsf_umma_pack_kernel(NsfNetGeom g, const float* __restrict__ fla
 struct UmmaState {
   uint8_t* wimg = nullptr;
   float* stash = nullptr;
+  long long* dbg = nullptr;   // [grid][16][16], allocated on first nsf_get_stage_cycles
+  int dbg_on = 0;
+  int last_grid = 0;
   int grid = 0;
 };
 
 }  // namespace
+
+#define NSF_TRY_INIT(ctx) do { int rc__ = nsf_umma_init(ctx); if (rc__ != NSF_OK) return rc__; } while (0)
 
 int nsf_umma_supported(const NsfNetGeom& g) { return g.H == KP && g.n_out == 3 && g.L >= 2 && g.L <= MAXL; }
 
@@ -626,7 +664,7 @@ int nsf_umma_init(NsfCtx* ctx) {
 void nsf_umma_free(NsfCtx* ctx) {
   UmmaState* s = (UmmaState*)ctx->umma;
   if (!s) return;
-  cudaFree(s->wimg); cudaFree(s->stash);
+  cudaFree(s->wimg); cudaFree(s->stash); if (s->dbg) cudaFree(s->dbg);
   delete s;
   ctx->umma = nullptr;
 }
@@ -650,11 +688,31 @@ int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_param
   a.stash = a.train ? s->stash : nullptr;
   a.scratch = a.train ? k.scratch : nullptr;
   a.n_pairs = (int)((k.n + 2 * P - 1) / (2 * P));
+  a.dbg = s->dbg_on ? s->dbg : nullptr;
   int grid = a.n_pairs < s->grid ? a.n_pairs : s->grid;
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }
   nsf_umma_jet_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
   NSF_CUDA_OK(cudaGetLastError());
   ++*launches;
+  s->last_grid = grid;
   *grid_out = grid;
+  return NSF_OK;
+}
+
+// Diagnostics: enable (out == NULL) or read back the per-warp cycle counters of the last tcgen05 launch, averaged
+// over CTAs: out[w*16 + k], w = warp 0..15, k: epilogue warps {fwd: MMA wait, work, fence, barrier, steps; rev: same};
+// issuer warp {weight wait, issue, MMA wait, barrier, steps}.
+int nsf_umma_stage_cycles(NsfCtx* ctx, double* out) {
+  NSF_TRY_INIT(ctx);
+  UmmaState* s = (UmmaState*)ctx->umma;
+  if (!s->dbg) { NSF_CUDA_OK(cudaMalloc((void**)&s->dbg, (size_t)s->grid * 256 * sizeof(long long))); NSF_CUDA_OK(cudaMemset(s->dbg, 0, (size_t)s->grid * 256 * sizeof(long long))); }
+  s->dbg_on = 1;
+  if (!out) return NSF_OK;
+  NSF_CUDA_OK(cudaDeviceSynchronize());
+  const int n = s->last_grid > 0 ? s->last_grid : 1;
+  long long* h = new long long[(size_t)n * 256];
+  if (cudaMemcpy(h, s->dbg, (size_t)n * 256 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) { delete[] h; nsf_set_error("cudaMemcpy failed"); return NSF_E_CUDA; }
+  for (int i = 0; i < 256; ++i) { double acc = 0; for (int c = 0; c < n; ++c) acc += (double)h[(size_t)c * 256 + i]; out[i] = acc / n; }
+  delete[] h;
   return NSF_OK;
 }
