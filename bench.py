@@ -131,7 +131,8 @@ def main():
     ap.add_argument("--cpu-n-f", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 tile-major, 3 tcgen05 layer-major")
+    ap.add_argument("--nt", type=int, default=0, help="tiles per super-batch of the layer-major kernel (0 = default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -161,6 +162,8 @@ def main():
         P = PysicsInformedNeuralNetwork(Re=1000, layers=4, hidden_size=120, N_f=args.n_f * world, bc_weight=10, eq_weight=1)
     if args.path:
         P._ctx.set_path(args.path)
+    if args.nt:
+        P._ctx.set_tiles_per_batch(args.nt)
     P.log_interval = 10 ** 9
     P.checkpoints = False
     P.set_boundary_data(cavity_boundary(513))
@@ -277,7 +280,7 @@ def main():
     peak = 0.5 * bf16_sust          # dense TF32 = 1/2 of the measured sustained bf16 (kernel timed inside a long step)
     info = P._ctx.info()
     cfg = workload_config(args)
-    cfg["kernel_path"] = "ffma" if info["path"] == 1 else "tcgen05-3xtf32"
+    cfg["kernel_path"] = {1: "ffma", 2: "tcgen05-3xtf32 tile-major", 3: "tcgen05-3xtf32 layer-major"}[info["path"]]
     line = {"metric": "collocation_pts_per_s (residual + weight gradient)", "value": value, "unit": "pts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,

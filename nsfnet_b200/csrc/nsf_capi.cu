@@ -107,6 +107,7 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   nsf_rt_free(ctx->e_buf); nsf_rt_free(ctx->ebar_buf);
 #ifndef NSF_EMU
   nsf_umma_free(ctx);
+  nsf_umma2_free(ctx);
   if (ctx->ev0) cudaEventDestroy((cudaEvent_t)ctx->ev0);
   if (ctx->ev1) cudaEventDestroy((cudaEvent_t)ctx->ev1);
 #endif
@@ -114,27 +115,34 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   return NSF_OK;
 }
 
-// kernel family the next collocation launch uses: 1 = FFMA, 2 = tcgen05
+// kernel family the next collocation launch uses: 1 = FFMA, 2 = tcgen05 tile-major, 3 = tcgen05 layer-major
 static int effective_path(const NsfCtx* ctx) {
 #ifdef NSF_EMU
   return 1;
 #else
   if (ctx->path == 1) return 1;
-  return nsf_umma_supported(ctx->main.g) ? 2 : 1;
+  if (!nsf_umma_supported(ctx->main.g)) return 1;
+  return ctx->path == 3 ? 3 : 2;
 #endif
 }
 
 extern "C" int nsf_set_path(NsfCtx* ctx, int path) {
-  if (!ctx || path < 0 || path > 2) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
+  if (!ctx || path < 0 || path > 3) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
 #ifdef NSF_EMU
-  if (path == 2) { nsf_set_error("tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE; }
+  if (path >= 2) { nsf_set_error("tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE; }
 #else
-  if (path == 2 && !nsf_umma_supported(ctx->main.g)) {
+  if (path >= 2 && !nsf_umma_supported(ctx->main.g)) {
     nsf_set_error("tcgen05 path covers hidden = 80 with 2..6 hidden layers; this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
     return NSF_E_SHAPE;
   }
 #endif
   ctx->path = path;
+  return NSF_OK;
+}
+
+extern "C" int nsf_set_tiles_per_batch(NsfCtx* ctx, int nt) {
+  if (!ctx || nt < 0 || nt > 8) { nsf_set_error("nsf_set_tiles_per_batch: nt must be 0 (default) .. 8"); return NSF_E_ARG; }
+  ctx->umma2_nt = nt;
   return NSF_OK;
 }
 
@@ -160,6 +168,10 @@ static int launch_jet(NsfCtx* ctx, NsfKernelArgs& a, const float* flat_main, int
   if (effective_path(ctx) == 2) {
     NSF_TRY(nsf_umma_init(ctx));
     return nsf_umma_launch(ctx, a, flat_main, grid, st, &ctx->launches);
+  }
+  if (effective_path(ctx) == 3) {
+    NSF_TRY(nsf_umma2_init(ctx));
+    return nsf_umma2_launch(ctx, a, flat_main, grid, st, &ctx->launches);
   }
 #endif
   (void)flat_main;
@@ -320,6 +332,10 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     NSF_TRY(nsf_umma_init(ctx));
     const long long pairs = (n_f + 15) / 16;
     grids[0] = (int)(pairs < ctx->sms ? pairs : ctx->sms);
+  }
+  if (n_f > 0 && effective_path(ctx) == 3) {
+    NSF_TRY(nsf_umma2_init(ctx));
+    grids[0] = nsf_umma2_grid(ctx, n_f, ctx->umma2_nt > 0 ? ctx->umma2_nt : 4);
   }
 #endif
   for (int b = 0; b < n_blocks; ++b) grids[1 + b] = blocks[b].n > 0 ? grid_for(ctx, M, 1, blocks[b].n) : 0;

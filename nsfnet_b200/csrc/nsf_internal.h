@@ -60,7 +60,9 @@ struct NsfCtx {
   float* e_buf = nullptr;     // [cap] EVM output at the collocation points
   float* ebar_buf = nullptr;  // [cap] d(loss)/d(e)
   long long cap = 0;
-  void* umma = nullptr;  // tcgen05 path state (nsf_umma.cu)
+  void* umma = nullptr;  // tcgen05 path state, tile-major kernel (nsf_umma_jet.cu)
+  void* umma2 = nullptr; // tcgen05 path state, layer-major kernel (nsf_umma_jet2.cu)
+  int umma2_nt = 0;      // tiles per super-batch of the layer-major kernel (0 = default)
   int timing = 0;        // bracket the dominant kernel with events (nsf_set_timing)
   void* ev0 = nullptr;
   void* ev1 = nullptr;
@@ -85,6 +87,10 @@ int nsf_umma_supported(const NsfNetGeom& g);
 int nsf_umma_init(NsfCtx* ctx);
 void nsf_umma_free(NsfCtx* ctx);
 int nsf_umma_stage_cycles(NsfCtx* ctx, double* out);
+int nsf_umma2_init(NsfCtx* ctx);
+void nsf_umma2_free(NsfCtx* ctx);
+int nsf_umma2_grid(const NsfCtx* ctx, long long n, int nt);
+int nsf_umma2_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 
 // flat parameter i of the packed image (host + device)

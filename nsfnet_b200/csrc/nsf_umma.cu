@@ -7,6 +7,8 @@
 //   variant 3 "forward/dgrad":  A = weight image (K-major, LBO = 128, SBO = one 8-row band),
 //                               B = activation / adjoint rows with the chunk stride padded to 144 B so that
 //                               the epilogue's per-neuron scalar stores are bank-conflict free
+//   variant 4 "A from TMEM"  :  A written to tensor memory with tcgen05.st (lane = row, column = K index), B as in
+//                               variant 3; tcgen05.mma reads A from TMEM and only B from shared memory
 // flag 16: 3xTF32 (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM).
 // Measured on B200: MN-major tf32 operands in the no-swizzle layout produce zeros (CUTLASS: "for mn-major
 // tf32 operands, SW128_32B is the only available smem layout"), so every contraction of the jet kernel is
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(128) nsf_selftest_kernel(SelftestArgs a) {
   // layouts ---------------------------------------------------------------------------------
   int a_mn, b_mn;
   uint32_t a_sbo, a_lbo, a_step, b_sbo, b_lbo, b_step, a_bytes, b_bytes;
-  if (a.variant == 3) {  // forward / dgrad: A rows j, K chunks 128 B apart; B rows n, K chunks 144 B apart
+  if (a.variant == 3 || a.variant == 4) {  // forward / dgrad: A rows j, K chunks 128 B apart; B rows n, K chunks 144 B apart
     a_mn = 0; a_lbo = 128; a_sbo = (uint32_t)(K / 4) * 128; a_step = 256; a_bytes = (uint32_t)(M / 8) * a_sbo;
     b_mn = 0; b_lbo = 144; b_sbo = (uint32_t)(K / 4) * 144; b_step = 288; b_bytes = (uint32_t)(N / 8) * b_sbo;
   } else {  // wgrad: A (j, n) K-major with point blocks as K chunks, B (k, n) likewise
@@ -71,7 +73,8 @@ __global__ void __launch_bounds__(128) nsf_selftest_kernel(SelftestArgs a) {
     *reinterpret_cast<float*>(b_lo + off) = lo;
   }
   uint32_t ncols = 32;
-  while ((int)ncols < N) ncols <<= 1;
+  const int need = a.variant == 4 ? N + 2 * K : N;
+  while ((int)ncols < need) ncols <<= 1;
   if (warp == 0) tmem_alloc(&tmem_base, ncols);
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   fence_async_smem();
@@ -80,7 +83,40 @@ __global__ void __launch_bounds__(128) nsf_selftest_kernel(SelftestArgs a) {
   tc_fence_after();
   const uint32_t tb = tmem_base;
 
-  if (tid == 0) {
+  if (a.variant == 4) {
+    // A -> TMEM: thread (row) writes its K values, hi at columns [N, N+K), lo at [N+K, N+2K)
+    for (int c0 = 0; c0 < K; c0 += 8) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = a.a[(size_t)tid * K + c0 + i];
+        split_tf32(v, hi[i], lo[i]);
+        if (!split3) { hi[i] = v; lo[i] = 0.f; }
+      }
+      tmem_st8(tb + ((uint32_t)(warp * 32) << 16) + (uint32_t)(N + c0), hi);
+      tmem_st8(tb + ((uint32_t)(warp * 32) << 16) + (uint32_t)(N + K + c0), lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+      const uint32_t leader = elect_one();
+      const uint32_t idesc = idesc_tf32(M, N, 0, 0);
+      const uint32_t bhi = desc_hi(b_sbo);
+      uint32_t acc = 0;
+      for (int ks = 0; ks < K / 8; ++ks) {
+        const uint32_t bh = desc_lo(smem_u32(b_hi) + ks * b_step, b_lbo), bl = desc_lo(smem_u32(b_lo) + ks * b_step, b_lbo);
+        const uint32_t ah = tb + (uint32_t)(N + ks * 8), al = tb + (uint32_t)(N + K + ks * 8);
+        if (split3) {
+          mma_tf32_ts_elect(tb, al, bh, bhi, idesc, acc, leader); acc = 1;
+          mma_tf32_ts_elect(tb, ah, bl, bhi, idesc, acc, leader);
+        }
+        mma_tf32_ts_elect(tb, ah, bh, bhi, idesc, acc, leader); acc = 1;
+      }
+      mma_commit_elect(&bar, leader);
+    }
+  } else if (tid == 0) {
     const uint32_t alb = a_lbo, asb = a_sbo, blb = b_lbo, bsb = b_sbo;
     const uint32_t idesc = idesc_tf32(M, N, a_mn, b_mn);
     uint32_t acc = 0;
@@ -116,8 +152,8 @@ __global__ void __launch_bounds__(128) nsf_selftest_kernel(SelftestArgs a) {
 extern "C" int nsf_selftest_umma(int device, int32_t variant, const float* a, const float* b, float* d, int32_t n, int32_t k,
                                  void* stream) {
   const int v = variant & 15, flags = variant & ~15;
-  if (!a || !b || !d || (v != 2 && v != 3) || (flags & ~16) || n < 16 || n > 256 || (n % 16) || k < 8 || (k % 8)) {
-    nsf_set_error("nsf_selftest_umma: bad argument (variant 2 or 3 [+16], n in [16,256] multiple of 16, k multiple of 8)");
+  if (!a || !b || !d || (v < 2 || v > 4) || (flags & ~16) || n < 16 || n > 256 || (n % 16) || k < 8 || (k % 8)) {
+    nsf_set_error("nsf_selftest_umma: bad argument (variant 2, 3 or 4 [+16], n in [16,256] multiple of 16, k multiple of 8)");
     return NSF_E_ARG;
   }
   cudaDeviceProp prop;
@@ -125,7 +161,7 @@ extern "C" int nsf_selftest_umma(int device, int32_t variant, const float* a, co
   if (prop.major != 10) { nsf_set_error("nsf_selftest_umma: device is not sm_100"); return NSF_E_ARCH; }
   NSF_CUDA_OK(cudaSetDevice(device));
   size_t a_bytes, b_bytes;
-  if (v == 3) { a_bytes = (size_t)16 * (k / 4) * 128; b_bytes = (size_t)(n / 8) * (k / 4) * 144; }
+  if (v == 3 || v == 4) { a_bytes = (size_t)16 * (k / 4) * 128; b_bytes = (size_t)(n / 8) * (k / 4) * 144; }
   else { a_bytes = (size_t)(k / 4) * 16 * 128; b_bytes = (size_t)(k / 4) * (n / 8) * 128; }
   const size_t smem = 2 * a_bytes + 2 * b_bytes + 1024;
   if (smem > 220 * 1024) { nsf_set_error("nsf_selftest_umma: operands do not fit in shared memory (%zu bytes)", smem); return NSF_E_SHAPE; }

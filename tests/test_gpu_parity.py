@@ -197,7 +197,8 @@ def test_full_size_properties(gu):
 # ---- tcgen05 (3xTF32) path: same bar as the FP32 path -------------------------------------------------
 @pytest.mark.parametrize("L,n,nb", [(6, 1333, 132), (2, 16, 8), (3, 5, 3), (6, 100000, 2052), (4, 777, 40)])
 @pytest.mark.parametrize("has_evm", [False, True])
-def test_umma_step_matches_oracle(gu, L, n, nb, has_evm):
+@pytest.mark.parametrize("path", [2, 3])
+def test_umma_step_matches_oracle(gu, L, n, nb, has_evm, path):
     H = 80
     rng = np.random.default_rng(L * 100 + n)
     md, ed = J.NetDesc(2, 3, L, H), J.NetDesc(2, 1, 4, 40)
@@ -210,13 +211,13 @@ def test_umma_step_matches_oracle(gu, L, n, nb, has_evm):
     phys = J.Physics(Re=1000., alpha_b=10., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
     r = J.step(pm, md, phys, x, y, xb, yb, ub, vb, evm_flat=pe if has_evm else None, evm_desc=ed if has_evm else None, w=w,
                vis_t_minus=vtm if has_evm else None)
-    abi = gu.Abi((2, 3, L, H), (2, 1, 4, 40) if has_evm else None, path=2)
+    abi = gu.Abi((2, 3, L, H), (2, 1, 4, 40) if has_evm else None, path=path)
     cp = _capi.physics(1000., alpha_evm=0.05, has_evm=has_evm, evm_trainable=has_evm, coord_scale=cs)
     o = abi.step(pm, cp, x, y, blocks=[(xb, yb, ub, vb, None, _bc(nb), _bc(nb), 0.)], params_evm=pe if has_evm else None, w=w,
                  vtm_in=vtm if has_evm else None)
-    assert o["info"]["path"] == 2
+    assert o["info"]["path"] == path
     errs = dict(grad=gu.rel(o["grad_main"], r.grad_main), eq=[gu.rel(o["resid"][k], r.eq[k]) for k in range(4 if has_evm else 3)])
-    print("umma", L, n, has_evm, errs)
+    print("umma path", path, L, n, has_evm, errs)
     assert errs["grad"] < TOL
     for k in range(4 if has_evm else 3):
         assert errs["eq"][k] < TOL
@@ -232,11 +233,12 @@ def test_umma_step_matches_oracle(gu, L, n, nb, has_evm):
     assert np.array_equal(o["grad_main"], o2["grad_main"])
 
 
-def test_umma_golden_ev_lag(gu, golden_dir):
+@pytest.mark.parametrize("path", [2, 3])
+def test_umma_golden_ev_lag(gu, golden_dir, path):
     g = np.load(os.path.join(golden_dir, "ev_re2000_lag.npz"))
     xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
     nb, n = xb.size, g["xf"].size
-    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40), path=2)
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40), path=path)
     vtm = g["vis_t_minus_init"]
     for k in range(int(g["steps"])):
         cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)

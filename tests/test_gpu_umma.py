@@ -17,7 +17,7 @@ def test_umma_kmajor_layouts(n, k):
     B = rng.standard_normal((n, k)).astype(np.float32)
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     a, b = torch.as_tensor(A).cuda(), torch.as_tensor(B).cuda()
-    for variant in (2, 3):          # 2: "n-contiguous" operand images (wgrad), 3: padded row images (forward / dgrad)
+    for variant in (2, 3, 4):       # 4: A operand from tensor memory; 2: "n-contiguous" operand images (wgrad), 3: padded row images (forward / dgrad)
         errs = {}
         for flags in (0, 16):
             d = torch.full((128, n), float("nan"), device="cuda")
