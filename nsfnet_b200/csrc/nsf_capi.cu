@@ -158,7 +158,7 @@ extern "C" int nsf_get_stage_cycles(NsfCtx* ctx, double* out) {
   (void)out; nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE;
 #else
   if (!nsf_umma_supported(ctx->main.g)) { nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not cover this net"); return NSF_E_SHAPE; }
-  return nsf_umma_stage_cycles(ctx, out);
+  return effective_path(ctx) == 3 ? nsf_umma2_stage_cycles(ctx, out) : nsf_umma_stage_cycles(ctx, out);
 #endif
 }
 

@@ -89,6 +89,7 @@ void nsf_umma_free(NsfCtx* ctx);
 int nsf_umma_stage_cycles(NsfCtx* ctx, double* out);
 int nsf_umma2_init(NsfCtx* ctx);
 void nsf_umma2_free(NsfCtx* ctx);
+int nsf_umma2_stage_cycles(NsfCtx* ctx, double* out);
 int nsf_umma2_grid(const NsfCtx* ctx, long long n, int nt);
 int nsf_umma2_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);

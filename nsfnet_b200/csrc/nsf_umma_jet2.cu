@@ -67,6 +67,7 @@ struct U2Args {
   float* scratch;
   int nt;                // tiles per super-batch
   long long n_sb;        // super-batches
+  long long* dbg;        // optional per-warp cycle counters [grid][16][16]
 };
 
 struct Misc2 {
@@ -212,22 +213,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
     const uint32_t leader = elect_one();
     uint32_t rph[2] = {0, 0}, dwph = 0;
     long long k = 0, bwd_stages = 0;
+    long long ic[4] = {0, 0, 0, 0}, t0 = 0, t1 = 0;    // ready wait, issue, dw wait, items
     for (long long gs = 0; gs < total_stages; ++gs) {
       const int sidx = (int)(gs % nstage);
       const bool bwd = sidx >= L;
       for (int i = 0; i < NT; ++i, ++k) {
         const int slot = (int)(k & 1);
+        if (a.dbg) t0 = clock64();
         mbar_wait(&misc->ready[slot], rph[slot]); rph[slot] ^= 1;
         tc_fence_after();
+        if (a.dbg) { t1 = clock64(); ic[0] += t1 - t0; t0 = t1; }
         issue_main(smem, tmem, slot, (int)(gs & 1), leader);
+        if (a.dbg) { t1 = clock64(); ic[1] += t1 - t0; t0 = t1; }
         if (bwd) {
           if (i == 0 && bwd_stages > 0) { mbar_wait(&misc->dwfree, dwph); dwph ^= 1; tc_fence_after(); }
+          if (a.dbg) { t1 = clock64(); ic[2] += t1 - t0; t0 = t1; }
           issue_wgrad(smem, tmem, slot, i == 0, leader);
         }
         mma_commit_elect(&misc->done[slot], leader);
+        if (a.dbg) { t1 = clock64(); ic[1] += t1 - t0; ic[3] += 1; }
       }
       if (bwd) ++bwd_stages;
     }
+    if (a.dbg && lane == 0)
+      for (int q = 0; q < 4; ++q) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + q] = ic[q];
   } else if ((warp & 3) != 3) {
     // =========================== epilogue warps ===========================
     Epi e;
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
     uint32_t dph[2] = {0, 0};
     bool first_flush = true;
 
+    long long ec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pre, fence+arrive, post (incl. MMA wait), stage end, items, MMA wait
     // item k -> (super-batch, stage, tile)
     auto pre = [&](long long k) {
       const long long gs = k / NT;
@@ -322,6 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
       }
     };
 
+    long long ec5_dummy = 0; (void)ec5_dummy;
     auto post = [&](long long k) {
       const long long gs = k / NT;
       const int i = (int)(k % NT), sidx = (int)(gs % nstage), slot = (int)(k & 1);
@@ -349,8 +360,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
           yv[pi] = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
         }
       }
+      long long tw = 0;
+      if (a.dbg) tw = clock64();
       mbar_wait(&misc->done[slot], dph[slot]); dph[slot] ^= 1;
       tc_fence_after();
+      if (a.dbg) ec[5] += clock64() - tw;
       float d[PPT][4];
       tmem_ld8(d_addr, &d[0][0]);
       tmem_ld4(d_addr + 8, &d[2][0]);
@@ -463,6 +477,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
       }
     };
 
+    long long t0 = 0, t1 = 0;
     if (total_items > 0) {
       load_weights(a, e, tmem, 0, 0);
       if (total_stages > 1) load_weights(a, e, tmem, 1 % nstage, 1);
@@ -471,13 +486,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
       tc_fence_before();
       mbar_arrive(&misc->ready[0]);
       for (long long k = 0; k < total_items; ++k) {
+        if (a.dbg) t0 = clock64();
         if (k + 1 < total_items) {
           pre(k + 1);
+          if (a.dbg) { t1 = clock64(); ec[0] += t1 - t0; t0 = t1; }
           fence_async_smem();
           tc_fence_before();
           mbar_arrive(&misc->ready[(k + 1) & 1]);
+          if (a.dbg) { t1 = clock64(); ec[1] += t1 - t0; t0 = t1; }
         }
         post(k);
+        if (a.dbg) { t1 = clock64(); ec[2] += t1 - t0; ec[4] += 1; t0 = t1; }
         if ((k + 1) % NT == 0) {                       // item k closes stage gs
           const long long gs = k / NT;
           const int sidx = (int)(gs % nstage);
@@ -504,10 +523,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet2_kernel(const U2Args
             load_weights(a, e, tmem, (int)((gs + 2) % nstage), (int)(gs & 1));
             tc_fence_before();
           }
+          if (a.dbg) { t1 = clock64(); ec[3] += t1 - t0; }
         }
       }
     }
     (void)first_flush;
+    if (a.dbg && lane == 0)
+      for (int q = 0; q < 8; ++q) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + q] = ec[q];
 
     // ---- CTA epilogue: thread-local partials -> this CTA's row ---------------------------------------------
     if (grow) {
@@ -592,6 +614,8 @@ struct Umma2State {
   float* wimg = nullptr;
   float* stash = nullptr;
   float* abar = nullptr;
+  long long* dbg = nullptr;
+  int dbg_on = 0, last_grid = 0;
   int grid = 0;
 };
 
@@ -616,7 +640,7 @@ int nsf_umma2_init(NsfCtx* ctx) {
 void nsf_umma2_free(NsfCtx* ctx) {
   Umma2State* s = (Umma2State*)ctx->umma2;
   if (!s) return;
-  cudaFree(s->wimg); cudaFree(s->stash); cudaFree(s->abar);
+  cudaFree(s->wimg); cudaFree(s->stash); cudaFree(s->abar); if (s->dbg) cudaFree(s->dbg);
   delete s;
   ctx->umma2 = nullptr;
 }
@@ -645,11 +669,29 @@ int nsf_umma2_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_para
   a.scratch = a.train ? k.scratch : nullptr;
   a.nt = ctx->umma2_nt > 0 && ctx->umma2_nt <= NT_MAX ? ctx->umma2_nt : 4;
   a.n_sb = (k.n + (long long)a.nt * P - 1) / ((long long)a.nt * P);
+  a.dbg = s->dbg_on ? s->dbg : nullptr;
   const int grid = nsf_umma2_grid(ctx, k.n, a.nt);
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }
   nsf_umma_jet2_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
   NSF_CUDA_OK(cudaGetLastError());
   ++*launches;
+  s->last_grid = grid;
   *grid_out = grid;
+  return NSF_OK;
+}
+
+int nsf_umma2_stage_cycles(NsfCtx* ctx, double* out) {
+  int rc = nsf_umma2_init(ctx);
+  if (rc != NSF_OK) return rc;
+  Umma2State* s = (Umma2State*)ctx->umma2;
+  if (!s->dbg) { NSF_CUDA_OK(cudaMalloc((void**)&s->dbg, (size_t)s->grid * 256 * sizeof(long long))); NSF_CUDA_OK(cudaMemset(s->dbg, 0, (size_t)s->grid * 256 * sizeof(long long))); }
+  s->dbg_on = 1;
+  if (!out) return NSF_OK;
+  NSF_CUDA_OK(cudaDeviceSynchronize());
+  const int n = s->last_grid > 0 ? s->last_grid : 1;
+  long long* h = new long long[(size_t)n * 256];
+  if (cudaMemcpy(h, s->dbg, (size_t)n * 256 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) { delete[] h; nsf_set_error("cudaMemcpy failed"); return NSF_E_CUDA; }
+  for (int i = 0; i < 256; ++i) { double acc = 0; for (int c = 0; c < n; ++c) acc += (double)h[(size_t)c * 256 + i]; out[i] = acc / n; }
+  delete[] h;
   return NSF_OK;
 }
