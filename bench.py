@@ -30,6 +30,11 @@ FLOPS_PER_PT = {"ev": 976_400.0, "ns": 1_305_840.0}      # algor
 EXEC_FLOPS_PER_PT = {"ev": 30 * 80 * 80 * 5 * 0.8 + 9840.0, "ns": 30 * 120 * 120 * 3 * 0.8}  # 4 streams carried (laplacian merged)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture of
+# this command line (profiles/r1_umma_v3_1M_ncu_summary.txt); keyed by (workload, kernel path, points per GPU)
+NCU_TRAFFIC_BYTES = {("ev", 2, 1_000_000): 74.904320e6 + 2.269425e9}
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -285,7 +290,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "adam_steps_per_s": adam_steps_s,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, info["path"], n)),
                          "kernel": "collocation jet step (fwd jet + residuals + reverse)", "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / ms_per_step, "flops_per_pt_algorithmic": FLOPS_PER_PT[args.workload],
                          "flops_per_pt_executed": EXEC_FLOPS_PER_PT[args.workload],
