@@ -251,6 +251,7 @@ __device__ __forceinline__ void flush_dw(const NsfNetGeom& g, float* grow, uint3
   }
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + OFF_MISC);
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     for (int pr = 0; pr < my_pairs; ++pr) {
       for (int step = 0; step < nsteps; ++step) {
         long long t0 = 0, t1 = 0;
-        if (a.dbg) t0 = clock64();
+        if (DBG) t0 = clock64();
         // (a) issue the MMAs whose operands were completed by the previous step's epilogue
         if (step >= 1) {
           const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
@@ -310,13 +311,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           if (s < nstage) {
             const int b = (int)(mma_stage & 1);
             if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
-            if (a.dbg) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
+            if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
             issue_stage(a, smem, tmem, s, pslot, b, (pr % FLUSH) == 0 && pslot == 0, leader);
             mma_commit_elect(&misc->mbar[pslot], leader);
             if (pslot == 1) { ++mma_stage; w_ready = false; }
           }
         }
-        if (a.dbg) { t1 = clock64(); icnt[1] += t1 - t0; t0 = t1; }
+        if (DBG) { t1 = clock64(); icnt[1] += t1 - t0; t0 = t1; }
         // (b) when slot B's MMAs of a stage have completed, its weight buffer is free: prefetch two stages ahead
         {
           const int slot = step & 1, s = step >> 1;
@@ -326,13 +327,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           }
         }
         __syncwarp();
-        if (a.dbg) { t1 = clock64(); icnt[2] += t1 - t0; t0 = t1; }
+        if (DBG) { t1 = clock64(); icnt[2] += t1 - t0; t0 = t1; }
         step_bar();
         tc_fence_after();
-        if (a.dbg) { t1 = clock64(); icnt[3] += t1 - t0; icnt[4] += 1; }
+        if (DBG) { t1 = clock64(); icnt[3] += t1 - t0; icnt[4] += 1; }
       }
     }
-    if (a.dbg && lane == 0) {
+    if (DBG && lane == 0) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = icnt[i];
     }
@@ -365,19 +366,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     for (int i = 0; i < MAXL; ++i) gb[i] = 0.f;
     float lossacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gbl[3] = {0.f, 0.f, 0.f};   // threads tid < P only
     uint32_t mphase[2] = {0, 0};
+    const size_t stash_slot_stride = (size_t)L * P * KP * 4;
+    const float* bias_ptr = pk + g.pk_b(1) + jj;                 // b_l[j] = bias_ptr[(l - 1) * bias_stride]
+    const size_t bias_stride = (size_t)(2 * g.HP * g.HP + g.HP);
+    const uint32_t d_base = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + e.sub * (4 * PPT));
     long long tcnt[10];      // [fwd | rev] x {MMA wait, work, fence, barrier, steps}
 #pragma unroll
     for (int i = 0; i < 10; ++i) tcnt[i] = 0;
 
     for (int pr = 0; pr < my_pairs; ++pr) {
       const long long pair = (long long)blockIdx.x + (long long)pr * gridDim.x;
+      const long long pA = pair * 2 * P;                                    // first point of slot A's tile; slot B follows
+      const long long rem = a.n - pA;
+      const int nvA = (int)(rem < 0 ? 0 : (rem < P ? rem : P)), nvB = (int)(rem - P < 0 ? 0 : (rem - P < P ? rem - P : P));
       for (int step = 0; step < nsteps; ++step) {
         const int slot = step & 1, s = step >> 1;
-        const long long p0 = (pair * 2 + slot) * P;                       // first point of this slot's tile
-        const int nvalid = (int)((a.n - p0) < 0 ? 0 : ((a.n - p0) < P ? (a.n - p0) : P));
+        const long long p0 = pA + slot * P;
+        const int nvalid = slot ? nvB : nvA;
         uint8_t* sb = smem + OFF_SLOT + (size_t)slot * SLOT;
-        float* stash_slot = stash_cta ? stash_cta + (size_t)slot * L * P * KP * 4 : nullptr;
-        const uint32_t d_addr = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + slot * NCOL + e.sub * (4 * PPT));
+        float* stash_slot = stash_cta ? stash_cta + (size_t)slot * stash_slot_stride : nullptr;
+        const uint32_t d_addr = d_base + (uint32_t)(slot * NCOL);
         // reverse stages: fetch the stashed pre-activations (L2) BEFORE waiting for the MMAs of this stage
         const int lrev = (s >= L) ? 2 * L - s - 1 : -1;                    // layer whose tanh is differentiated (s = L: L-1)
         float4 st_l[PPT], st_lm1[PPT];
@@ -390,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         }
         // operands that come from L2 (the L1 is ~1 KB next to 227 KB of shared memory): issue the loads before the wait
         float bias_s = 0.f, xv[PPT], yv[PPT];
-        if (e.active && s >= 1 && s < L) bias_s = __ldg(pk + g.pk_b(s) + e.j);
+        if (e.active && s >= 1 && s < L) bias_s = __ldg(bias_ptr + (size_t)(s - 1) * bias_stride);
         if (s == 0 || s == 2 * L - 1) {
 #pragma unroll
           for (int pi = 0; pi < PPT; ++pi) {
@@ -401,9 +409,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         }
         const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
         long long t0 = 0, t1 = 0;
-        if (a.dbg) t0 = clock64();
+        if (DBG) t0 = clock64();
         if (s >= 1) { mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1; tc_fence_after(); }
-        if (a.dbg) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
+        if (DBG) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
 
         if (s == 0) {
           // ---- layer 0 (K = 2) -------------------------------------------------------------
@@ -533,12 +541,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             }
           }
         }
-        if (a.dbg) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
+        if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
         fence_async_smem();
         tc_fence_before();
-        if (a.dbg) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; }
+        if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; }
         step_bar();
-        if (a.dbg) { t0 = clock64(); tcnt[cls + 3] += t0 - t1; tcnt[cls + 4] += 1; }
+        if (DBG) { t0 = clock64(); tcnt[cls + 3] += t0 - t1; tcnt[cls + 4] += 1; }
       }
       if (a.train && grow && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
         // every MMA of this pair has completed (its barriers were waited on above); the next pair's first
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       }
     }
 
-    if (a.dbg && lane == 0) {
+    if (DBG && lane == 0) {
 #pragma unroll
       for (int i = 0; i < 10; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = tcnt[i];
     }
@@ -655,7 +663,8 @@ int nsf_umma_init(NsfCtx* ctx) {
   if (s->grid > ctx->main.rows) s->grid = ctx->main.rows;
   NSF_CUDA_OK(cudaMalloc((void**)&s->wimg, (size_t)(2 * g.L - 1) * WBUF));
   NSF_CUDA_OK(cudaMalloc((void**)&s->stash, (size_t)s->grid * 2 * g.L * P * KP * 4 * sizeof(float)));
-  NSF_CUDA_OK(cudaFuncSetAttribute(nsf_umma_jet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NSF_CUDA_OK(cudaFuncSetAttribute(nsf_umma_jet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  NSF_CUDA_OK(cudaFuncSetAttribute(nsf_umma_jet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   ctx->ws_bytes += (long long)(2 * g.L - 1) * WBUF + (long long)s->grid * 2 * g.L * P * KP * 16;
   ctx->umma = s;
   return NSF_OK;
@@ -691,7 +700,8 @@ int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_param
   a.dbg = s->dbg_on ? s->dbg : nullptr;
   int grid = a.n_pairs < s->grid ? a.n_pairs : s->grid;
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }
-  nsf_umma_jet_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  if (a.dbg) nsf_umma_jet_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  else nsf_umma_jet_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
   NSF_CUDA_OK(cudaGetLastError());
   ++*launches;
   s->last_grid = grid;
