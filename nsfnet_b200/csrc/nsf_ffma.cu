@@ -11,8 +11,9 @@ int nsf_ffma_pt(int ns, int hp) { return (ns == 4 && hp > 80) ? 16 : 32; }
 // ---------------------------------------------------------------------------------------------
 // CUDA
 // ---------------------------------------------------------------------------------------------
+// threads per CTA = (HP/4) * (PT/4): <4,32> serves HP <= 80 (160 threads), <4,16> HP <= 128 (128), <1,32> HP <= 128 (256)
 template <int NS, int PT>
-__global__ void __launch_bounds__(256) nsf_ffma_kernel(const NsfKernelArgs a) {
+__global__ void __launch_bounds__(NS == 1 ? 256 : (PT == 32 ? 160 : 128)) nsf_ffma_kernel(const NsfKernelArgs a) {
   extern __shared__ __align__(16) float nsf_smem[];
   nsf_cta_program<NS, PT>(a, nsf_smem, (int)blockIdx.x, (int)gridDim.x, (int)blockDim.x);
 }
