@@ -3,8 +3,8 @@
 //
 // Orientation: TMEM lane = neuron, TMEM column = 4*point + stream (streams 0, x, y, laplacian), i.e. the
 // MMA is  D[neuron j, (p,s)] = sum_k W[j,k] * a_s[p,k]  with M = 128 (80 real rows), N = 4*P, K = 80.
-// An epilogue thread owns one neuron of a quarter of the tile's points: it reads its 4 stream values of a
-// point with ONE tcgen05.ld, applies the tanh jet on FFMA / MUFU and writes the next layer's operands.
+// An epilogue thread owns one neuron for two points of the tile: it reads its 4 stream values of both points
+// with ONE tcgen05.ld, applies the tanh jet on FFMA / MUFU and writes the next layer's operands.
 //
 // One CTA per SM (persistent), 15 warps.  A warp may only touch the TMEM lane quadrant (warp id & 3), and the 80
 // neurons live in quadrants 0-2, so:
@@ -15,15 +15,20 @@
 // one slot, the epilogue warps work on the other slot.  One CTA-wide barrier per step.
 //
 // Per tile the stages are  s = 0: layer 0 (K = 2, FFMA);  s = 1..L-1: hidden layer s (fwd MMA);  s = L:
-// output layer (MMA) + residuals + adjoint seeds;  s = L+1..2L-1: reverse of hidden layer l = 2L-s
+// output layer (MMA, M = 64) + residuals + adjoint seeds;  s = L+1..2L-1: reverse of hidden layer l = 2L-s
 // (dgrad MMA -> adjoint of layer l-1, wgrad MMA accumulating dW_l in TMEM for the whole kernel).
+// The kernel is a template on the layer count: the stage sequence is unrolled, every stage is straight-line code
+// with immediate offsets (round-1 profile: 57 % of the issued instructions of the run-time-L version were integer /
+// branch overhead and the epilogue warps were issue bound).
 //
-// Every MMA operand is K-major, no swizzle (measured: MN-major tf32 needs the 32B-atom swizzle):
-//   weight image (A operand)       : rows j, 16-byte K chunks 128 B apart, 8-row bands 2560 B apart
-//   "R" image (B operand, fwd/dgrad): rows n = 4p+s, contraction over neurons; chunk stride padded to
-//                                     144 B so that the per-neuron scalar stores are conflict free
-//   "C" image (A / B of wgrad)      : rows = neuron, contraction over n; one 16-byte chunk = the 4 streams
-//                                     of a point (a single st.shared.v4 per thread and point)
+// Operand images in shared memory:
+//   weight image (A operand, fwd / dgrad): K-major, no swizzle: rows j, 16-byte K chunks 128 B apart, 8-row bands 2560 B apart
+//   "R" image (B operand, fwd / dgrad)   : rows n = 4p+s, contraction over neurons, MN-MAJOR so that a thread stores the 4
+//                                          streams of a point with one st.shared.v4.  tf32 MN-major exists only as descriptor
+//                                          layout type 1 (128-byte swizzle, 32-byte atoms); its address map was measured with
+//                                          scripts/probe_mma.cu:  (k/4)*SBO + (k%4)*128 + ((n/8) ^ (k%4))*32 + (n%8)*4
+//   "C" image (A / B of wgrad)           : K-major, no swizzle: rows = neuron, contraction over n; one 16-byte chunk = the
+//                                          4 streams of a point (a single st.shared.v4 per thread and point)
 #include "nsf_internal.h"
 #include "nsf_tc.cuh"
 #include "nsf_math.cuh"
@@ -48,22 +53,22 @@ constexpr int FLUSH = 32;         // tile pairs between flushes of the TMEM weig
 constexpr uint32_t W_SBO = (KP / 4) * 128;      // 2560: 8-row band of a weight image
 constexpr uint32_t IMG = (KP / 8) * W_SBO;      // 25600: one weight image (hi or lo)
 constexpr uint32_t WBUF = 2 * IMG;              // hi | lo
-constexpr uint32_t R_LBO = 144, R_SBO = (KP / 4) * R_LBO;   // 2880
-constexpr uint32_t RB = (NCOL / 8) * R_SBO;     // 11520: one R image
+constexpr uint32_t R_ATOM = 512;                // 4 neurons x 128 B (32 columns n) of an R image
+constexpr uint32_t RB = (KP / 4) * R_ATOM;      // 10240: one R image
 constexpr uint32_t C_SP = (KP / 8) * 128;       // 1280: point block of a C image
 constexpr uint32_t CB = P * C_SP;               // 10240: one C image
-constexpr uint32_t SLOT = 2 * RB + 4 * CB;      // 64000: R hi, R lo, ZC hi, ZC lo, AC hi, AC lo
+constexpr uint32_t SLOT = 2 * RB + 4 * CB;      // 61440: R hi, R lo, ZC hi, ZC lo, AC hi, AC lo
 constexpr uint32_t OFF_SLOT = 2 * WBUF;         // 102400
-constexpr uint32_t OFF_MISC = OFF_SLOT + 2 * SLOT;   // 230400
+constexpr uint32_t OFF_MISC = OFF_SLOT + 2 * SLOT;   // 225280
 constexpr uint32_t MISC = 1536;
-constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;     // 231936 <= 232448
+constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;     // 226816 <= 232448
+static_assert(OFF_SLOT % 1024 == 0 && SLOT % 1024 == 0, "R images must keep the 512-byte swizzle phase");
 
 struct UArgs {
   NsfNetGeom g;
   const float* pk;       // FFMA packed image: layer 0, biases, output layer rows
   const uint8_t* wimg;   // (2L-1) weight images of WBUF bytes: WF_1..WF_L, WB_{L-1}..WB_1
   const float* x; const float* y; long long n;
-  int train;             // 0: residuals only
   const float* e_in; const float* vtm_in; float* vtm_out; const float* w;
   float inv_Re, vis_t0, alpha_evm, cs1, cs2, k4, c_eq;
   int has_evm;
@@ -80,7 +85,7 @@ struct Misc {
   uint32_t tmem_base;
   uint32_t pad[3];
   float ov[2][P][16];    // outputs / output adjoints [slot][p][4*s + o]
-  float red[P][12];
+  float red[P][12];      // per-point-lane loss sums and output-bias gradient partials
 };
 static_assert(sizeof(Misc) <= MISC, "misc region too small");
 
@@ -95,38 +100,37 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // step barrier: epilogue warps + issuer warp (the two spare warps of quadrant 3 do not take part)
 __device__ __forceinline__ void step_bar() { asm volatile("bar.sync 2, %0;" ::"n"(NEPI + 32) : "memory"); }
 
-__device__ __forceinline__ void st4(uint8_t* p, float a, float b, float c, float d) {
-  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+// shared-memory stores through 32-bit shared-window addresses (immediate offsets fold into the instruction)
+__device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void st1(uint8_t* p, float a) { *reinterpret_cast<float*>(p) = a; }
 
-// image index (0-based) used by MMA stage s (1..2L-1) of a tile
-__device__ __forceinline__ int img_of_stage(int s) { return s - 1; }
+__host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t layout_type) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29); }
 
-// ---- issuer: all MMAs of stage s for one slot (executed by the whole issuer warp, see mma_tf32_elect) ----
-__device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint32_t tmem, int s, int slot, int wbuf, bool zero_dw,
-                                            uint32_t leader) {
-  const int L = a.g.L;
-  const uint32_t wa = smem_u32(smem) + (uint32_t)wbuf * WBUF;
-  const uint32_t sb = smem_u32(smem) + OFF_SLOT + (uint32_t)slot * SLOT;
+// ---- issuer: all MMAs of stage s for one slot (executed by the whole issuer warp, see mma_tf32_elect2) ----
+template <int L>
+__device__ __forceinline__ void issue_stage(uint32_t smem_base, uint32_t tmem, int s, int slot, int wbuf, bool zero_dw, uint32_t leader) {
+  const uint32_t wa = smem_base + (uint32_t)wbuf * WBUF;
+  const uint32_t sb = smem_base + OFF_SLOT + (uint32_t)slot * SLOT;
   const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
   {  // forward (s <= L) or dgrad (s > L): D[128, 4P] = Wimg[128, 80] * R[4P, 80]^T
     // The tensor core truncates when it adds into the fp32 accumulator (measured: -2e-8 relative per MMA for
     // same-sign sums).  Issue the 2^-11-sized correction products first, while the accumulator is still small,
     // and the hi*hi products last: 10 full-magnitude accumulations per layer instead of 30.
-    const uint32_t idesc = idesc_tf32(128, NCOL, 0, 0);
-    constexpr uint32_t AHI = desc_hi(W_SBO), BHI = desc_hi(R_SBO);
+    // The output layer (s = L) has 3 real rows: M = 64 halves the operand fetch of its MMAs.
+    const uint32_t idesc = (s == L) ? idesc_tf32(64, NCOL, 0, 1) : idesc_tf32(128, NCOL, 0, 1);
+    constexpr uint32_t AHI = desc_hi(W_SBO), BHI = desc_hi_t(R_ATOM, 1);
     const uint32_t ah0 = desc_lo(wa, 128), al0 = desc_lo(wa + IMG, 128);
-    const uint32_t bh0 = desc_lo(sb, R_LBO), bl0 = desc_lo(sb + RB, R_LBO);
+    const uint32_t bh0 = desc_lo(sb, 1024), bl0 = desc_lo(sb + RB, 1024);
 #pragma unroll
     for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_LBO) >> 4);
+      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
       mma_tf32_elect2(d_col, al0 + da, AHI, bh0 + db, BHI, idesc, ks > 0, leader);
       mma_tf32_elect2(d_col, ah0 + da, AHI, bl0 + db, BHI, idesc, 1, leader);
     }
 #pragma unroll
     for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_LBO) >> 4);
+      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
       mma_tf32_elect2(d_col, ah0 + da, AHI, bh0 + db, BHI, idesc, 1, leader);
     }
   }
@@ -150,83 +154,51 @@ __device__ __forceinline__ void issue_stage(const UArgs& a, uint8_t* smem, uint3
 
 // ---- epilogue helpers ---------------------------------------------------------------------------
 struct Epi {
-  int j, sub, q, lane;
+  int j, sub, q;
   bool active;           // j < KP
   uint32_t lane_addr;    // TMEM lane field of this warp's quadrant
-  uint32_t r_off;        // byte offset of (n = 0, j) in an R image
-  uint32_t c_off;        // byte offset of (j, point 0) in a C image
-  uint32_t r_base[PPT];  // byte offset of (n = 4p, j) in an R image for this thread's points
-  uint32_t c_base[PPT];  // byte offset of (j, point p) in a C image
-  uint32_t s_base[PPT];  // float offset of (layer 0, point p, neuron j) in a stash slot
+  uint32_t r_off;        // byte offset of this thread's float4 (point pi = 0; pi = 1: + 16) in an R image
+  uint32_t c_off;        // byte offset of this thread's float4 (point pi = 0; pi = 1: + C_SP) in a C image
 };
 
-// tanh jet of one point: z -> activations; returns t
-__device__ __forceinline__ void jet_fwd(const float z[4], float& t, float& ax, float& ay, float& al) {
-  t = nsf_tanh_fast(z[0]);
-  const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1;
-  ax = d1 * z[1]; ay = d1 * z[2];
-  al = fmaf(d2, fmaf(z[1], z[1], z[2] * z[2]), d1 * z[3]);
-}
-
-// write the 4 streams of point p (tile-local index) for neuron j into an R image pair
-__device__ __forceinline__ void store_RC(uint8_t* rh, uint8_t* zh, const Epi& e, int pi, const float v[4], bool do_r, bool do_c) {
-  float hi[4], lo[4];
+__device__ __forceinline__ void split4(const float v[4], float hi[4], float lo[4]) {
 #pragma unroll
   for (int s = 0; s < 4; ++s) split_tf32_fast(v[s], hi[s], lo[s]);
-  if (do_r) {
-    const uint32_t base = e.r_base[pi];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) { st1(rh + base + s * 16, hi[s]); st1(rh + RB + base + s * 16, lo[s]); }
-  }
-  if (do_c) {
-    const uint32_t off = e.c_base[pi];
-    st4(zh + off, hi[0], hi[1], hi[2], hi[3]);
-    st4(zh + CB + off, lo[0], lo[1], lo[2], lo[3]);
-  }
+}
+// the 4 streams of point pi -> R image pair at `rimg` (hi; lo follows RB bytes later)
+__device__ __forceinline__ void store_R(uint32_t rimg, const Epi& e, int pi, const float hi[4], const float lo[4]) {
+  sts4(rimg + e.r_off + pi * 16, hi[0], hi[1], hi[2], hi[3]);
+  sts4(rimg + RB + e.r_off + pi * 16, lo[0], lo[1], lo[2], lo[3]);
+}
+// ... -> C image pair at `cimg` (hi; lo follows CB bytes later)
+__device__ __forceinline__ void store_C(uint32_t cimg, const Epi& e, int pi, const float hi[4], const float lo[4]) {
+  sts4(cimg + e.c_off + pi * C_SP, hi[0], hi[1], hi[2], hi[3]);
+  sts4(cimg + CB + e.c_off + pi * C_SP, lo[0], lo[1], lo[2], lo[3]);
 }
 
-// forward epilogue of layer l for this thread's points: z (pre-activations incl. bias) -> R image (+ stash)
-__device__ __forceinline__ void epi_forward(const UArgs& a, uint8_t* slot_base, const Epi& e, float* stash_slot, int l,
-                                            float z[PPT][4]) {
-#pragma unroll
-  for (int pi = 0; pi < PPT; ++pi) {
-    float t, v[4];
-    jet_fwd(z[pi], t, v[1], v[2], v[3]);
-    v[0] = t;
-    if (a.train) __stcs(reinterpret_cast<float4*>(stash_slot + (size_t)l * (P * KP * 4) + e.s_base[pi]), make_float4(t, z[pi][1], z[pi][2], z[pi][3]));
-    store_RC(slot_base, nullptr, e, pi, v, true, false);
-  }
+// tanh jet of one point: z -> activations
+__device__ __forceinline__ void jet_fwd(const float z[4], float v[4]) {
+  const float t = nsf_tanh_fast(z[0]);
+  const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1;
+  v[0] = t; v[1] = d1 * z[1]; v[2] = d1 * z[2];
+  v[3] = fmaf(d2, fmaf(z[1], z[1], z[2] * z[2]), d1 * z[3]);
 }
-
-// reverse epilogue of layer l: adjoints of the activations (ab) -> pre-activation adjoints; writes the R and C
-// images of zb and (l >= 1) the C image of a^{l-1}; st_l / st_lm1 are the stashed (t, zx, zy, z_lap) of layers l, l-1
-__device__ __forceinline__ void epi_reverse(uint8_t* slot_base, const Epi& e, int l, const float ab[PPT][4], float zb[PPT][4],
-                                            float act[PPT][4], const float4* st_l, const float4* st_lm1) {
-  uint8_t* zh = slot_base + 2 * RB;
-  uint8_t* ch = zh + 2 * CB;
-#pragma unroll
-  for (int pi = 0; pi < PPT; ++pi) {
-    const float4 st = st_l[pi];
-    const float t = st.x, zx = st.y, zy = st.z, zl_ = st.w;
-    const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1, d3 = -2.f * d1 * fmaf(-3.f * t, t, 1.f);
-    const float a0 = ab[pi][0], ax = ab[pi][1], ay = ab[pi][2], al = ab[pi][3];
-    const float q = fmaf(zx, zx, zy * zy);
-    zb[pi][3] = al * d1;
-    zb[pi][1] = fmaf(ax, d1, 2.f * al * d2 * zx);
-    zb[pi][2] = fmaf(ay, d1, 2.f * al * d2 * zy);
-    zb[pi][0] = fmaf(a0, d1, fmaf(ax * d2, zx, fmaf(ay * d2, zy, al * fmaf(d3, q, d2 * zl_))));
-    // the layer's own activations (for the output-layer weight gradient when l = L-1)
-    act[pi][0] = t; act[pi][1] = d1 * zx; act[pi][2] = d1 * zy; act[pi][3] = fmaf(d2, q, d1 * zl_);
-    if (l >= 1) {
-      store_RC(slot_base, zh, e, pi, zb[pi], true, true);
-      const float4 s1 = st_lm1[pi];
-      const float e1 = fmaf(-s1.x, s1.x, 1.f), e2 = -2.f * s1.x * e1;
-      float av[4];
-      av[0] = s1.x; av[1] = e1 * s1.y; av[2] = e1 * s1.z;
-      av[3] = fmaf(e2, fmaf(s1.y, s1.y, s1.z * s1.z), e1 * s1.w);
-      store_RC(nullptr, ch, e, pi, av, false, true);
-    }
-  }
+// activations of a layer from its stashed (t, zx, zy, z_lap)
+__device__ __forceinline__ void act_from_stash(const float4 s, float a[4]) {
+  const float d1 = fmaf(-s.x, s.x, 1.f), d2 = -2.f * s.x * d1;
+  a[0] = s.x; a[1] = d1 * s.y; a[2] = d1 * s.z;
+  a[3] = fmaf(d2, fmaf(s.y, s.y, s.z * s.z), d1 * s.w);
+}
+// adjoint through tanh: ab (adjoint of the activations), stash of the layer -> zb
+__device__ __forceinline__ void zbar_from(const float4 st, const float ab[4], float zb[4]) {
+  const float t = st.x, zx = st.y, zy = st.z, zl = st.w;
+  const float d1 = fmaf(-t, t, 1.f), d2 = -2.f * t * d1, d3 = -2.f * d1 * fmaf(-3.f * t, t, 1.f);
+  const float q = fmaf(zx, zx, zy * zy);
+  const float c = 2.f * ab[3] * d2;
+  zb[3] = ab[3] * d1;
+  zb[1] = fmaf(ab[1], d1, c * zx);
+  zb[2] = fmaf(ab[2], d1, c * zy);
+  zb[0] = fmaf(ab[0], d1, fmaf(ab[1] * d2, zx, fmaf(ab[2] * d2, zy, ab[3] * fmaf(d3, q, d2 * zl))));
 }
 
 // dW_l accumulators (TMEM lane = j, columns (l-1)*80 + k) -> this CTA's gradient row.  Bounds the number of
@@ -251,24 +223,26 @@ __device__ __forceinline__ void flush_dw(const NsfNetGeom& g, float* grow, uint3
   }
 }
 
-template <bool DBG>
+template <int L, bool TRAIN, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + OFF_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const NsfNetGeom& g = a.g;
-  const int L = g.L;
-  const int nstage = a.train ? 2 * L : L + 1;       // stages per tile
-  const int nsteps = 2 * nstage;                    // steps per tile pair
+  constexpr int NSTAGE = TRAIN ? 2 * L : L + 1;     // stages per tile
+  constexpr int NSTEPS = 2 * NSTAGE;                // steps per tile pair
+  const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) tmem_alloc(&misc->tmem_base, 512);
   if (tid == 0) {
+    if (smem_base & 1023u) __trap();                // the swizzled R images assume a 1 KB aligned window
     mbar_init(&misc->mbar[0], 1); mbar_init(&misc->mbar[1], 1);
     mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
     mbar_fence_init();
   }
-  // zero the operand slots once: padded rows / stale data must at least be finite-free of surprises
+  // zero the operand slots once (the M = 128 operand fetch reads 48 rows past the 80 real ones) and the loss sums
   for (uint32_t i = tid * 16; i < 2 * SLOT; i += NTHREADS * 16) *reinterpret_cast<float4*>(smem + OFF_SLOT + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < P * 12) (&misc->red[0][0])[tid] = 0.f;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -282,13 +256,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     // The whole warp walks the loop convergently with warp-uniform state; one elected lane issues the TMA
     // copies, the MMAs and the commits.
     const uint32_t leader = elect_one();
-    const long long total_mma_stages = (long long)my_pairs * (nstage - 1);
+    const long long total_mma_stages = (long long)my_pairs * (NSTAGE - 1);
     long long loaded = 0;      // weight images requested so far (one per MMA stage, in stage order)
     uint32_t wphase[2] = {0, 0};
     auto load_next = [&]() {
       if (loaded >= total_mma_stages) return;
       const int b = (int)(loaded & 1);
-      const int img = (int)(loaded % (nstage - 1));
+      const int img = (int)(loaded % (NSTAGE - 1));
       if (leader) {
         mbar_expect_tx(&misc->wbar[b], WBUF);
         tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
@@ -301,18 +275,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     bool w_ready = false;
     long long icnt[5] = {0, 0, 0, 0, 0};   // weight wait, issue, MMA wait, barrier, steps
     for (int pr = 0; pr < my_pairs; ++pr) {
-      for (int step = 0; step < nsteps; ++step) {
+#pragma unroll 1
+      for (int step = 0; step < NSTEPS; ++step) {
         long long t0 = 0, t1 = 0;
         if (DBG) t0 = clock64();
         // (a) issue the MMAs whose operands were completed by the previous step's epilogue
         if (step >= 1) {
           const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
           const int s = ps + 1;                                     // stage to issue for that slot
-          if (s < nstage) {
+          if (s < NSTAGE) {
             const int b = (int)(mma_stage & 1);
             if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
             if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
-            issue_stage(a, smem, tmem, s, pslot, b, (pr % FLUSH) == 0 && pslot == 0, leader);
+            issue_stage<L>(smem_base, tmem, s, pslot, b, (pr % FLUSH) == 0 && pslot == 0, leader);
             mma_commit_elect(&misc->mbar[pslot], leader);
             if (pslot == 1) { ++mma_stage; w_ready = false; }
           }
@@ -340,36 +315,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
   } else if ((warp & 3) != 3) {
     // =========================== epilogue warps ===========================
     Epi e;
-    e.lane = lane; e.q = warp & 3; e.sub = warp >> 2;
+    e.q = warp & 3; e.sub = warp >> 2;
     e.j = e.q * 32 + lane;
     e.active = e.j < KP;
     e.lane_addr = (uint32_t)(e.q * 32) << 16;
-    e.r_off = (uint32_t)(e.j >> 2) * R_LBO + (uint32_t)(e.j & 3) * 4;
-    e.c_off = (uint32_t)(e.j >> 3) * 128 + (uint32_t)(e.j & 7) * 16;
-#pragma unroll
-    for (int pi = 0; pi < PPT; ++pi) {
-      const int p = e.sub * PPT + pi;
-      e.r_base[pi] = (uint32_t)(p >> 1) * R_SBO + (uint32_t)((p & 1) * 4) * 16 + e.r_off;
-      e.c_base[pi] = (uint32_t)p * C_SP + e.c_off;
-      e.s_base[pi] = (uint32_t)((p * KP + (e.active ? e.j : 0)) * 4);
-    }
+    e.r_off = (uint32_t)(e.j >> 2) * R_ATOM + (uint32_t)(e.j & 3) * 128 + (uint32_t)((e.sub ^ (e.j & 3)) * 32);
+    e.c_off = (uint32_t)(2 * e.sub) * C_SP + (uint32_t)(e.j >> 3) * 128 + (uint32_t)(e.j & 7) * 16;
     const int jj = e.active ? e.j : 0;
     const float* pk = a.pk;
     const float w0x = __ldg(pk + g.pk_w0x() + jj), w0y = __ldg(pk + g.pk_w0y() + jj), b0 = __ldg(pk + g.pk_b0() + jj);
     const float wl0 = __ldg(pk + g.pk_wl() + jj), wl1 = __ldg(pk + g.pk_wl() + g.HP + jj), wl2 = __ldg(pk + g.pk_wl() + 2 * g.HP + jj);
-    float* stash_cta = a.stash ? a.stash + (size_t)blockIdx.x * 2 * L * P * KP * 4 : nullptr;
-    float* grow = a.scratch ? a.scratch + (size_t)blockIdx.x * g.gs_row() : nullptr;
+    float bias[MAXL];      // b_l[j], l = 1..L-1
+#pragma unroll
+    for (int l = 1; l < MAXL; ++l) bias[l] = (l < L) ? __ldg(pk + g.pk_b(l) + jj) : 0.f;
+    const float bo = (e.q == 0 && lane < 3) ? __ldg(pk + g.pk_bl() + lane) : 0.f;
+    // this thread's float4 of (slot 0, layer 0, point 2*sub); + slot*L*P*KP + l*P*KP + pi*KP float4s
+    float4* stash_thr = TRAIN ? reinterpret_cast<float4*>(a.stash) + (size_t)blockIdx.x * (2 * L * P * KP) + (size_t)(2 * e.sub) * KP + jj : nullptr;
+    float* grow = TRAIN ? a.scratch + (size_t)blockIdx.x * g.gs_row() : nullptr;
     // per-thread gradient partials (this neuron, this thread's share of the points)
     float gw0x = 0.f, gw0y = 0.f, gwl[3] = {0.f, 0.f, 0.f};
     float gb[MAXL];
 #pragma unroll
     for (int i = 0; i < MAXL; ++i) gb[i] = 0.f;
-    float lossacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gbl[3] = {0.f, 0.f, 0.f};   // threads tid < P only
-    uint32_t mphase[2] = {0, 0};
-    const size_t stash_slot_stride = (size_t)L * P * KP * 4;
-    const float* bias_ptr = pk + g.pk_b(1) + jj;                 // b_l[j] = bias_ptr[(l - 1) * bias_stride]
-    const size_t bias_stride = (size_t)(2 * g.HP * g.HP + g.HP);
+    uint32_t mphases = 0;                                          // bit slot: parity to wait for on mbar[slot]
     const uint32_t d_base = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + e.sub * (4 * PPT));
+    const uint32_t slot0 = smem_base + OFF_SLOT;
     long long tcnt[10];      // [fwd | rev] x {MMA wait, work, fence, barrier, steps}
 #pragma unroll
     for (int i = 0; i < 10; ++i) tcnt[i] = 0;
@@ -379,176 +349,206 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       const long long pA = pair * 2 * P;                                    // first point of slot A's tile; slot B follows
       const long long rem = a.n - pA;
       const int nvA = (int)(rem < 0 ? 0 : (rem < P ? rem : P)), nvB = (int)(rem - P < 0 ? 0 : (rem - P < P ? rem - P : P));
-      for (int step = 0; step < nsteps; ++step) {
-        const int slot = step & 1, s = step >> 1;
-        const long long p0 = pA + slot * P;
-        const int nvalid = slot ? nvB : nvA;
-        uint8_t* sb = smem + OFF_SLOT + (size_t)slot * SLOT;
-        float* stash_slot = stash_cta ? stash_cta + (size_t)slot * stash_slot_stride : nullptr;
-        const uint32_t d_addr = d_base + (uint32_t)(slot * NCOL);
-        // reverse stages: fetch the stashed pre-activations (L2) BEFORE waiting for the MMAs of this stage
-        const int lrev = (s >= L) ? 2 * L - s - 1 : -1;                    // layer whose tanh is differentiated (s = L: L-1)
-        float4 st_l[PPT], st_lm1[PPT];
-        if (a.train && lrev >= 0 && e.active) {
 #pragma unroll
-          for (int pi = 0; pi < PPT; ++pi) {
-            st_l[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + (size_t)lrev * (P * KP * 4) + e.s_base[pi]));
-            if (lrev >= 1) st_lm1[pi] = __ldcs(reinterpret_cast<const float4*>(stash_slot + (size_t)(lrev - 1) * (P * KP * 4) + e.s_base[pi]));
-          }
-        }
-        // operands that come from L2 (the L1 is ~1 KB next to 227 KB of shared memory): issue the loads before the wait
-        float bias_s = 0.f, xv[PPT], yv[PPT];
-        if (e.active && s >= 1 && s < L) bias_s = __ldg(bias_ptr + (size_t)(s - 1) * bias_stride);
-        if (s == 0 || s == 2 * L - 1) {
-#pragma unroll
-          for (int pi = 0; pi < PPT; ++pi) {
-            const int p = e.sub * PPT + pi;
-            xv[pi] = p < nvalid ? __ldg(a.x + p0 + p) : 0.f;
-            yv[pi] = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
-          }
-        }
-        const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
-        long long t0 = 0, t1 = 0;
-        if (DBG) t0 = clock64();
-        if (s >= 1) { mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1; tc_fence_after(); }
-        if (DBG) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
-
-        if (s == 0) {
-          // ---- layer 0 (K = 2) -------------------------------------------------------------
-          if (e.active) {
-            float z[PPT][4];
+      for (int s = 0; s < NSTAGE; ++s) {
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          const long long p0 = pA + slot * P;
+          const int nvalid = slot ? nvB : nvA;
+          const uint32_t sb = slot0 + (uint32_t)slot * SLOT;
+          float4* st_slot = TRAIN ? stash_thr + (size_t)slot * (L * P * KP) : nullptr;
+          const uint32_t d_addr = d_base + (uint32_t)(slot * NCOL);
+          // reverse stages: fetch the stashed pre-activations (L2) BEFORE waiting for the MMAs of this stage
+          const bool is_rev = TRAIN && s >= L;
+          const int lrev = 2 * L - s - 1;                                   // layer whose tanh is differentiated (s = L: L-1)
+          float4 st_l[PPT], st_lm1[PPT];
+          if (is_rev && e.active) {
 #pragma unroll
             for (int pi = 0; pi < PPT; ++pi) {
-              z[pi][0] = fmaf(w0x, xv[pi], fmaf(w0y, yv[pi], b0)); z[pi][1] = w0x; z[pi][2] = w0y; z[pi][3] = 0.f;
+              st_l[pi] = __ldcs(st_slot + lrev * (P * KP) + pi * KP);
+              if (lrev >= 1) st_lm1[pi] = __ldcs(st_slot + (lrev - 1) * (P * KP) + pi * KP);
             }
-            epi_forward(a, sb, e, stash_slot, 0, z);
           }
-        } else if (s < L) {
-          // ---- hidden layer s forward --------------------------------------------------------
-          float z[PPT][4];
-          tmem_ld8(d_addr, &z[0][0]);
-          tmem_ld_wait();
-          if (e.active) {
-#pragma unroll
-            for (int pi = 0; pi < PPT; ++pi) z[pi][0] += bias_s;
-            epi_forward(a, sb, e, stash_slot, s, z);
-          }
-        } else if (s == L) {
-          // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
-          float o[PPT][4];
-          tmem_ld8(d_addr, &o[0][0]);
-          tmem_ld_wait();
-          if (e.q == 0 && lane < 3) {
-            const float bo = __ldg(pk + g.pk_bl() + lane);
+          float xv[PPT], yv[PPT];
+          if (s == 0 || (TRAIN && s == 2 * L - 1)) {
 #pragma unroll
             for (int pi = 0; pi < PPT; ++pi) {
               const int p = e.sub * PPT + pi;
-              misc->ov[slot][p][0 * 4 + lane] = o[pi][0] + bo;
-              misc->ov[slot][p][1 * 4 + lane] = o[pi][1];
-              misc->ov[slot][p][2 * 4 + lane] = o[pi][2];
-              misc->ov[slot][p][3 * 4 + lane] = o[pi][3];
+              xv[pi] = p < nvalid ? __ldg(a.x + p0 + p) : 0.f;
+              yv[pi] = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
             }
           }
-          epi_bar();
-          if (tid < P) {
-            const int p = tid;
-            const bool ok = p < nvalid;
-            const long long gp = p0 + p;
-            float* ov = misc->ov[slot][p];
-            const float u = ov[0], v = ov[1];
-            const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
-            const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
-            const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
-            float ee = 0.f, vis = 0.f;
-            if (a.has_evm) {
-              ee = ok ? __ldg(a.e_in + gp) : 0.f;
-              vis = a.vis_t0;
-              if (a.vtm_in && ok) vis = fminf(a.vis_t0, __ldg(a.vtm_in + gp));
-            }
-            const float nu = a.inv_Re + vis;
-            const float eq1 = (u * ux + v * uy) + px - nu * ul;
-            const float eq2 = (u * vx + v * vy) + py - nu * vl;
-            const float eq3 = ux + vy;
-            const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
-            const float w = (a.w && ok) ? __ldg(a.w + gp) : 1.f;
-            if (ok) {
-              lossacc[0] += w * eq1 * eq1; lossacc[1] += w * eq2 * eq2; lossacc[2] += w * eq3 * eq3; lossacc[3] += w * eq4 * eq4;
-              lossacc[4] += vis; lossacc[5] += 1.f;
-              if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
-              if (a.vis_t_out) a.vis_t_out[gp] = vis;
-              if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
-            }
-            if (a.train) {
-              const float cw = ok ? a.c_eq * w : 0.f;
-              const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
-              const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
-              const float g3 = 2.f * cw * eq3;
-              const float g4 = a.k4 * cw * eq4;
-              ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
-              ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
-              ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
-              ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
-              gbl[0] += ov[0]; gbl[1] += ov[1]; gbl[2] += ov[2];
-              if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
-            }
+          const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
+          long long t0 = 0, t1 = 0;
+          if (DBG) t0 = clock64();
+          if (s >= 1) {
+            mbar_wait(&misc->mbar[slot], (mphases >> slot) & 1u);
+            mphases ^= 1u << slot;
+            tc_fence_after();
           }
-          if (a.train) {
-            epi_bar();
+          if (DBG) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
+
+          if (s == 0) {
+            // ---- layer 0 (K = 2) -------------------------------------------------------------
             if (e.active) {
-              float ab[PPT][4], zb[PPT][4], act[PPT][4];
 #pragma unroll
               for (int pi = 0; pi < PPT; ++pi) {
-                const float* ov = misc->ov[slot][e.sub * PPT + pi];
-#pragma unroll
-                for (int st = 0; st < 4; ++st) ab[pi][st] = fmaf(ov[st * 4 + 0], wl0, fmaf(ov[st * 4 + 1], wl1, ov[st * 4 + 2] * wl2));
+                const float z[4] = {fmaf(w0x, xv[pi], fmaf(w0y, yv[pi], b0)), w0x, w0y, 0.f};
+                float v[4], hi[4], lo[4];
+                jet_fwd(z, v);
+                if (TRAIN) __stcs(st_slot + pi * KP, make_float4(v[0], z[1], z[2], z[3]));
+                split4(v, hi, lo);
+                store_R(sb, e, pi, hi, lo);
               }
-              epi_reverse(sb, e, L - 1, ab, zb, act, st_l, st_lm1);
+            }
+          } else if (s < L) {
+            // ---- hidden layer s forward --------------------------------------------------------
+            float z[PPT][4];
+            tmem_ld8(d_addr, &z[0][0]);
+            tmem_ld_wait();
+            if (e.active) {
+#pragma unroll
+              for (int pi = 0; pi < PPT; ++pi) {
+                z[pi][0] += bias[s];
+                float v[4], hi[4], lo[4];
+                jet_fwd(z[pi], v);
+                if (TRAIN) __stcs(st_slot + s * (P * KP) + pi * KP, make_float4(v[0], z[pi][1], z[pi][2], z[pi][3]));
+                split4(v, hi, lo);
+                store_R(sb, e, pi, hi, lo);
+              }
+            }
+          } else if (s == L) {
+            // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
+            float o[PPT][4];
+            tmem_ld8(d_addr, &o[0][0]);
+            tmem_ld_wait();
+            if (e.q == 0 && lane < 3) {
+#pragma unroll
+              for (int pi = 0; pi < PPT; ++pi) {
+                const int p = e.sub * PPT + pi;
+                misc->ov[slot][p][0 * 4 + lane] = o[pi][0] + bo;
+                misc->ov[slot][p][1 * 4 + lane] = o[pi][1];
+                misc->ov[slot][p][2 * 4 + lane] = o[pi][2];
+                misc->ov[slot][p][3 * 4 + lane] = o[pi][3];
+              }
+            }
+            epi_bar();
+            if (tid < P) {
+              const int p = tid;
+              const bool ok = p < nvalid;
+              const long long gp = p0 + p;
+              float* ov = misc->ov[slot][p];
+              float* red = misc->red[p];
+              const float u = ov[0], v = ov[1];
+              const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
+              const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
+              const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
+              float ee = 0.f, vis = 0.f;
+              if (a.has_evm) {
+                ee = ok ? __ldg(a.e_in + gp) : 0.f;
+                vis = a.vis_t0;
+                if (a.vtm_in && ok) vis = fminf(a.vis_t0, __ldg(a.vtm_in + gp));
+              }
+              const float nu = a.inv_Re + vis;
+              const float eq1 = (u * ux + v * uy) + px - nu * ul;
+              const float eq2 = (u * vx + v * vy) + py - nu * vl;
+              const float eq3 = ux + vy;
+              const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
+              const float w = (a.w && ok) ? __ldg(a.w + gp) : 1.f;
+              if (ok) {
+                red[0] += w * eq1 * eq1; red[1] += w * eq2 * eq2; red[2] += w * eq3 * eq3; red[3] += w * eq4 * eq4;
+                red[4] += vis; red[5] += 1.f;
+                if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
+                if (a.vis_t_out) a.vis_t_out[gp] = vis;
+                if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
+              }
+              if (TRAIN) {
+                const float cw = ok ? a.c_eq * w : 0.f;
+                const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
+                const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
+                const float g3 = 2.f * cw * eq3;
+                const float g4 = a.k4 * cw * eq4;
+                ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
+                ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
+                ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
+                ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
+                red[6] += ov[0]; red[7] += ov[1]; red[8] += ov[2];
+                if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
+              }
+            }
+            if (TRAIN) {
+              epi_bar();
+              if (e.active) {
+                float sb0 = 0.f;
+#pragma unroll
+                for (int pi = 0; pi < PPT; ++pi) {
+                  const float4* ov4 = reinterpret_cast<const float4*>(misc->ov[slot][e.sub * PPT + pi]);
+                  float ab[4], zb[4], act[4], hi[4], lo[4];
+                  float4 ovs[4];
+#pragma unroll
+                  for (int st = 0; st < 4; ++st) {
+                    ovs[st] = ov4[st];
+                    ab[st] = fmaf(ovs[st].x, wl0, fmaf(ovs[st].y, wl1, ovs[st].z * wl2));
+                  }
+                  zbar_from(st_l[pi], ab, zb);
+                  act_from_stash(st_l[pi], act);
+#pragma unroll
+                  for (int st = 0; st < 4; ++st) {
+                    gwl[0] = fmaf(ovs[st].x, act[st], gwl[0]);
+                    gwl[1] = fmaf(ovs[st].y, act[st], gwl[1]);
+                    gwl[2] = fmaf(ovs[st].z, act[st], gwl[2]);
+                  }
+                  sb0 += zb[0];
+                  if (L >= 2) {
+                    split4(zb, hi, lo);
+                    store_R(sb, e, pi, hi, lo);
+                    store_C(sb + 2 * RB, e, pi, hi, lo);
+                    float av[4];
+                    act_from_stash(st_lm1[pi], av);
+                    split4(av, hi, lo);
+                    store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
+                  }
+                }
+                gb[L - 1] += sb0;
+              }
+            }
+          } else {
+            // ---- reverse: D holds the adjoint of layer l's activations, l = 2L - s - 1 ------------------
+            const int l = (2 * L - s - 1) >= 0 ? (2 * L - s - 1) : 0;
+            float ab[PPT][4];
+            tmem_ld8(d_addr, &ab[0][0]);
+            tmem_ld_wait();
+            if (e.active) {
               float sb0 = 0.f;
 #pragma unroll
               for (int pi = 0; pi < PPT; ++pi) {
-                const float* ov = misc->ov[slot][e.sub * PPT + pi];
-#pragma unroll
-                for (int st = 0; st < 4; ++st) {
-                  gwl[0] = fmaf(ov[st * 4 + 0], act[pi][st], gwl[0]);
-                  gwl[1] = fmaf(ov[st * 4 + 1], act[pi][st], gwl[1]);
-                  gwl[2] = fmaf(ov[st * 4 + 2], act[pi][st], gwl[2]);
+                float zb[4], hi[4], lo[4];
+                zbar_from(st_l[pi], ab[pi], zb);
+                sb0 += zb[0];
+                if (l >= 1) {
+                  split4(zb, hi, lo);
+                  store_R(sb, e, pi, hi, lo);
+                  store_C(sb + 2 * RB, e, pi, hi, lo);
+                  float av[4];
+                  act_from_stash(st_lm1[pi], av);
+                  split4(av, hi, lo);
+                  store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
+                } else {
+                  gw0x += fmaf(zb[0], xv[pi], zb[1]); gw0y += fmaf(zb[0], yv[pi], zb[2]);
                 }
-                sb0 += zb[pi][0];
               }
-#pragma unroll
-              for (int i = 0; i < MAXL; ++i) if (i == L - 1) gb[i] += sb0;
+              gb[l] += sb0;
             }
           }
-        } else {
-          // ---- reverse: D holds the adjoint of layer l's activations, l = 2L - s - 1 ------------------
-          const int l = lrev;
-          float ab[PPT][4];
-          tmem_ld8(d_addr, &ab[0][0]);
-          tmem_ld_wait();
-          if (e.active) {
-            float zb[PPT][4], act[PPT][4];
-            epi_reverse(sb, e, l, ab, zb, act, st_l, st_lm1);
-            float sb0 = 0.f;
-#pragma unroll
-            for (int pi = 0; pi < PPT; ++pi) sb0 += zb[pi][0];
-#pragma unroll
-            for (int i = 0; i < MAXL; ++i) if (i == l) gb[i] += sb0;
-            if (l == 0) {
-#pragma unroll
-              for (int pi = 0; pi < PPT; ++pi) {
-                gw0x += fmaf(zb[pi][0], xv[pi], zb[pi][1]); gw0y += fmaf(zb[pi][0], yv[pi], zb[pi][2]);
-              }
-            }
-          }
+          if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
+          fence_async_smem();
+          tc_fence_before();
+          if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; }
+          step_bar();
+          if (DBG) { t0 = clock64(); tcnt[cls + 3] += t0 - t1; tcnt[cls + 4] += 1; }
         }
-        if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
-        fence_async_smem();
-        tc_fence_before();
-        if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; }
-        step_bar();
-        if (DBG) { t0 = clock64(); tcnt[cls + 3] += t0 - t1; tcnt[cls + 4] += 1; }
       }
-      if (a.train && grow && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
+      if (TRAIN && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
         // every MMA of this pair has completed (its barriers were waited on above); the next pair's first
         // weight-gradient MMA is issued several CTA barriers from here
         tc_fence_after();
@@ -562,22 +562,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       for (int i = 0; i < 10; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = tcnt[i];
     }
     // ---- CTA epilogue: thread-local gradient partials and loss sums -> this CTA's row -------------
-    if (grow) {
+    if (a.scratch) {
+      float* growx = a.scratch + (size_t)blockIdx.x * g.gs_row();
       float* redf = reinterpret_cast<float*>(smem + OFF_SLOT);   // operand slots are free now: [NSUB-1][KP][16]
-      if (e.sub >= 1 && e.active) {
+      if (TRAIN && e.sub >= 1 && e.active) {
         float* r = redf + ((e.sub - 1) * KP + e.j) * 16;
         r[0] = gw0x; r[1] = gw0y; r[2] = gwl[0]; r[3] = gwl[1]; r[4] = gwl[2];
 #pragma unroll
         for (int i = 0; i < MAXL; ++i) r[5 + i] = gb[i];
       }
-      if (tid < P) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) misc->red[tid][k] = lossacc[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) misc->red[tid][6 + k] = gbl[k];
-      }
       epi_bar();
-      if (a.train && e.sub == 0 && e.active) {
+      if (TRAIN && e.sub == 0 && e.active) {
         float r[5 + MAXL];
 #pragma unroll
         for (int i = 0; i < 5 + MAXL; ++i) {
@@ -586,26 +581,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           for (int q = 0; q < NSUB - 1; ++q) r[i] += redf[(q * KP + e.j) * 16 + i];
         }
         const int j = e.j;
-        grow[g.gs_w0x() + j] = gw0x + r[0];
-        grow[g.gs_w0y() + j] = gw0y + r[1];
-        grow[g.gs_b0() + j] = gb[0] + r[5];
-        grow[g.gs_wl() + j] = gwl[0] + r[2];
-        grow[g.gs_wl() + g.HP + j] = gwl[1] + r[3];
-        grow[g.gs_wl() + 2 * g.HP + j] = gwl[2] + r[4];
-        grow[g.gs_wl() + 3 * g.HP + j] = 0.f;
+        growx[g.gs_w0x() + j] = gw0x + r[0];
+        growx[g.gs_w0y() + j] = gw0y + r[1];
+        growx[g.gs_b0() + j] = gb[0] + r[5];
+        growx[g.gs_wl() + j] = gwl[0] + r[2];
+        growx[g.gs_wl() + g.HP + j] = gwl[1] + r[3];
+        growx[g.gs_wl() + 2 * g.HP + j] = gwl[2] + r[4];
+        growx[g.gs_wl() + 3 * g.HP + j] = 0.f;
 #pragma unroll
         for (int l = 1; l < MAXL; ++l)
-          if (l < L) grow[g.gs_b(l) + j] = gb[l] + r[5 + l];
+          if (l < L) growx[g.gs_b(l) + j] = gb[l] + r[5 + l];
       }
       if (tid < NSF_LOSS_SLOTS) {
         float v = 0.f;
         if (tid < 6) for (int p = 0; p < P; ++p) v += misc->red[p][tid];
-        grow[g.gs_loss() + tid] = v;
+        growx[g.gs_loss() + tid] = v;
       }
-      if (a.train && tid < 4) {
+      if (TRAIN && tid < 4) {
         float v = 0.f;
         if (tid < 3) for (int p = 0; p < P; ++p) v += misc->red[p][6 + tid];
-        grow[g.gs_bl() + tid] = v;
+        growx[g.gs_bl() + tid] = v;
       }
     }
   }
@@ -654,6 +649,22 @@ struct UmmaState {
 
 int nsf_umma_supported(const NsfNetGeom& g) { return g.H == KP && g.n_out == 3 && g.L >= 2 && g.L <= MAXL; }
 
+typedef void (*JetKernel)(const UArgs);
+template <int L>
+static JetKernel jet_kernel_of(bool train, bool dbg) {
+  if (!train) return nsf_umma_jet_kernel<L, false, false>;
+  return dbg ? nsf_umma_jet_kernel<L, true, true> : nsf_umma_jet_kernel<L, true, false>;
+}
+static JetKernel jet_kernel(int L, bool train, bool dbg) {
+  switch (L) {
+    case 2: return jet_kernel_of<2>(train, dbg);
+    case 3: return jet_kernel_of<3>(train, dbg);
+    case 4: return jet_kernel_of<4>(train, dbg);
+    case 5: return jet_kernel_of<5>(train, dbg);
+    default: return jet_kernel_of<6>(train, dbg);
+  }
+}
+
 int nsf_umma_init(NsfCtx* ctx) {
   if (ctx->umma) return NSF_OK;
   if (!nsf_umma_supported(ctx->main.g)) { nsf_set_error("tcgen05 path covers hidden = 80, 2..6 hidden layers"); return NSF_E_SHAPE; }
@@ -663,8 +674,9 @@ int nsf_umma_init(NsfCtx* ctx) {
   if (s->grid > ctx->main.rows) s->grid = ctx->main.rows;
   NSF_CUDA_OK(cudaMalloc((void**)&s->wimg, (size_t)(2 * g.L - 1) * WBUF));
   NSF_CUDA_OK(cudaMalloc((void**)&s->stash, (size_t)s->grid * 2 * g.L * P * KP * 4 * sizeof(float)));
-  NSF_CUDA_OK(cudaFuncSetAttribute(nsf_umma_jet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  NSF_CUDA_OK(cudaFuncSetAttribute(nsf_umma_jet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  for (int train = 0; train < 2; ++train)
+    for (int dbg = 0; dbg <= train; ++dbg)
+      NSF_CUDA_OK(cudaFuncSetAttribute(jet_kernel(g.L, train != 0, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   ctx->ws_bytes += (long long)(2 * g.L - 1) * WBUF + (long long)s->grid * 2 * g.L * P * KP * 16;
   ctx->umma = s;
   return NSF_OK;
@@ -689,19 +701,19 @@ int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_param
   ++*launches;
   UArgs a;
   a.g = g; a.pk = k.pk; a.wimg = s->wimg; a.x = k.x; a.y = k.y; a.n = k.n;
-  a.train = k.mode == NSF_MODE_JET_STEP ? 1 : 0;
+  const bool train = k.mode == NSF_MODE_JET_STEP;
   a.e_in = k.e_in; a.vtm_in = k.vtm_in; a.vtm_out = k.vtm_out; a.w = k.w;
   a.inv_Re = k.inv_Re; a.vis_t0 = k.vis_t0; a.alpha_evm = k.alpha_evm; a.cs1 = k.cs1; a.cs2 = k.cs2; a.k4 = k.k4; a.c_eq = k.c_eq;
   a.has_evm = k.has_evm;
   a.resid_out = k.resid_out; a.vis_t_out = k.vis_t_out; a.ebar_out = k.ebar_out;
-  a.stash = a.train ? s->stash : nullptr;
-  a.scratch = a.train ? k.scratch : nullptr;
+  a.stash = train ? s->stash : nullptr;
+  a.scratch = train ? k.scratch : nullptr;
   a.n_pairs = (int)((k.n + 2 * P - 1) / (2 * P));
   a.dbg = s->dbg_on ? s->dbg : nullptr;
   int grid = a.n_pairs < s->grid ? a.n_pairs : s->grid;
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }
-  if (a.dbg) nsf_umma_jet_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
-  else nsf_umma_jet_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+  if (!train) a.dbg = nullptr;
+  jet_kernel(g.L, train, a.dbg != nullptr)<<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
   NSF_CUDA_OK(cudaGetLastError());
   ++*launches;
   s->last_grid = grid;
