@@ -9,10 +9,13 @@
 // One CTA per SM (persistent), 15 warps.  A warp may only touch the TMEM lane quadrant (warp id & 3), and the 80
 // neurons live in quadrants 0-2, so:
 //   warps 4*sub + q, q = 0..2, sub = 0..3 : epilogue (quadrant q, points 2*sub, 2*sub+1 of the tile) -- 12 warps
-//   warp 3                                : issuer (elected lane): TMA bulk loads of the weight images, tcgen05.mma, commit
-//   warps 7, 11                           : spare (quadrant 3 holds only padding rows)
+//   warp 3                                : issuer (elected lane): tcgen05.mma, tcgen05.commit
+//   warp 7                                : weight producer (one lane): TMA bulk loads of the per-stage weight images
+//   warp 11                               : spare (quadrant 3 holds only padding rows)
 // Two point tiles ("slots" A, B; P = 8 points each) are in flight: while the tensor pipe runs the MMAs of
-// one slot, the epilogue warps work on the other slot.  One CTA-wide barrier per step.
+// one slot, the epilogue warps work on the other slot.  There is no CTA-wide barrier in the steady state: the
+// warps are coupled by mbarriers only (ready: epilogue -> issuer, mbar: MMAs done -> epilogue, wbar / wfree:
+// weight buffer full / free), so the issuer queues the next slot's MMAs while the previous ones still execute.
 //
 // Per tile the stages are  s = 0: layer 0 (K = 2, FFMA);  s = 1..L-1: hidden layer s (fwd MMA);  s = L:
 // output layer (MMA, M = 64) + residuals + adjoint seeds;  s = L+1..2L-1: reverse of hidden layer l = 2L-s
@@ -80,8 +83,10 @@ struct UArgs {
 };
 
 struct Misc {
-  uint64_t mbar[2];      // MMA completion per slot
-  uint64_t wbar[2];      // weight image landed per buffer
+  uint64_t mbar[2];      // "done": the slot's MMAs have completed (tcgen05.commit)
+  uint64_t wbar[2];      // weight image landed in buffer b (TMA complete_tx)
+  uint64_t ready[2];     // the slot's operands are written and its previous results consumed (one arrival per epilogue warp)
+  uint64_t wfree[2];     // every MMA reading weight buffer b has completed (tcgen05.commit)
   uint32_t tmem_base;
   uint32_t pad[3];
   float ov[2][P][16];    // outputs / output adjoints [slot][p][4*s + o]
@@ -97,8 +102,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
-// step barrier: epilogue warps + issuer warp (the two spare warps of quadrant 3 do not take part)
-__device__ __forceinline__ void step_bar() { asm volatile("bar.sync 2, %0;" ::"n"(NEPI + 32) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // shared-memory stores through 32-bit shared-window addresses (immediate offsets fold into the instruction)
 __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
@@ -238,6 +244,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     if (smem_base & 1023u) __trap();                // the swizzled R images assume a 1 KB aligned window
     mbar_init(&misc->mbar[0], 1); mbar_init(&misc->mbar[1], 1);
     mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
+    mbar_init(&misc->ready[0], NEPI / 32); mbar_init(&misc->ready[1], NEPI / 32);
+    mbar_init(&misc->wfree[0], 1); mbar_init(&misc->wfree[1], 1);
     mbar_fence_init();
   }
   // zero the operand slots once (the M = 128 operand fetch reads 48 rows past the 80 real ones) and the loss sums
@@ -253,64 +261,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 
   if (warp == ISSUER_WARP) {
     // =========================== issuer warp ===========================
-    // The whole warp walks the loop convergently with warp-uniform state; one elected lane issues the TMA
-    // copies, the MMAs and the commits.
+    // No CTA-wide barrier in the steady state: the epilogue warps hand a slot's operands over through `ready`,
+    // results come back through tcgen05.commit on `mbar`; as long as the epilogue keeps up the tensor pipe never
+    // drains between stages.  The whole warp walks the loop convergently with warp-uniform state; one elected lane
+    // issues the MMAs and the commits.
     const uint32_t leader = elect_one();
-    const long long total_mma_stages = (long long)my_pairs * (NSTAGE - 1);
-    long long loaded = 0;      // weight images requested so far (one per MMA stage, in stage order)
-    uint32_t wphase[2] = {0, 0};
-    auto load_next = [&]() {
-      if (loaded >= total_mma_stages) return;
-      const int b = (int)(loaded & 1);
-      const int img = (int)(loaded % (NSTAGE - 1));
-      if (leader) {
-        mbar_expect_tx(&misc->wbar[b], WBUF);
-        tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
-      }
-      ++loaded;
-    };
-    load_next(); load_next();
-    long long mma_stage = 0;   // MMA stages fully issued (both slots) so far
-    uint32_t mphase[2] = {0, 0};
-    bool w_ready = false;
-    long long icnt[5] = {0, 0, 0, 0, 0};   // weight wait, issue, MMA wait, barrier, steps
+    uint32_t rphases = 0, wphases = 0;     // bit = slot / weight buffer: parity to wait for
+    uint32_t stage_ctr = 0;                // MMA stages issued so far (selects the weight buffer)
+    long long icnt[5] = {0, 0, 0, 0, 0};   // weight wait, issue, operand wait, -, stage-slots
     for (int pr = 0; pr < my_pairs; ++pr) {
 #pragma unroll 1
-      for (int step = 0; step < NSTEPS; ++step) {
-        long long t0 = 0, t1 = 0;
-        if (DBG) t0 = clock64();
-        // (a) issue the MMAs whose operands were completed by the previous step's epilogue
-        if (step >= 1) {
-          const int pslot = (step - 1) & 1, ps = (step - 1) >> 1;   // previous step's (slot, stage)
-          const int s = ps + 1;                                     // stage to issue for that slot
-          if (s < NSTAGE) {
-            const int b = (int)(mma_stage & 1);
-            if (!w_ready) { mbar_wait(&misc->wbar[b], wphase[b]); wphase[b] ^= 1; w_ready = true; }
-            if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
-            issue_stage<L>(smem_base, tmem, s, pslot, b, (pr % FLUSH) == 0 && pslot == 0, leader);
-            mma_commit_elect(&misc->mbar[pslot], leader);
-            if (pslot == 1) { ++mma_stage; w_ready = false; }
-          }
+      for (int s = 1; s < NSTAGE; ++s) {
+        const uint32_t b = stage_ctr & 1u;
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          long long t0 = 0, t1 = 0;
+          if (DBG) t0 = clock64();
+          mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u); rphases ^= 1u << slot;
+          if (DBG) { t1 = clock64(); icnt[2] += t1 - t0; t0 = t1; }
+          if (slot == 0) { mbar_wait(&misc->wbar[b], (wphases >> b) & 1u); wphases ^= 1u << b; }
+          tc_fence_after();
+          if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
+          issue_stage<L>(smem_base, tmem, s, slot, (int)b, (pr % FLUSH) == 0 && slot == 0, leader);
+          mma_commit_elect(&misc->mbar[slot], leader);
+          if (slot == 1) mma_commit_elect(&misc->wfree[b], leader);
+          __syncwarp();
+          if (DBG) { t1 = clock64(); icnt[1] += t1 - t0; icnt[4] += 1; }
         }
-        if (DBG) { t1 = clock64(); icnt[1] += t1 - t0; t0 = t1; }
-        // (b) when slot B's MMAs of a stage have completed, its weight buffer is free: prefetch two stages ahead
-        {
-          const int slot = step & 1, s = step >> 1;
-          if (s >= 1) {
-            mbar_wait(&misc->mbar[slot], mphase[slot]); mphase[slot] ^= 1;
-            if (slot == 1) load_next();
-          }
-        }
-        __syncwarp();
-        if (DBG) { t1 = clock64(); icnt[2] += t1 - t0; t0 = t1; }
-        step_bar();
-        tc_fence_after();
-        if (DBG) { t1 = clock64(); icnt[3] += t1 - t0; icnt[4] += 1; }
+        ++stage_ctr;
       }
     }
     if (DBG && lane == 0) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = icnt[i];
+    }
+  } else if (warp == ISSUER_WARP + 4) {
+    // =========================== weight producer (one lane) ===========================
+    // streams the per-stage weight images (hi | lo, 51 200 B) into the double buffer with one bulk TMA copy each
+    if (lane == 0) {
+      const long long total = (long long)my_pairs * (NSTAGE - 1);
+      int img = 0;
+      for (long long i = 0; i < total; ++i) {
+        const int b = (int)(i & 1);
+        if (i >= 2) mbar_wait(&misc->wfree[b], (uint32_t)(((i >> 1) - 1) & 1));
+        mbar_expect_tx(&misc->wbar[b], WBUF);
+        tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
+        if (++img == NSTAGE - 1) img = 0;
+      }
     }
   } else if ((warp & 3) != 3) {
     // =========================== epilogue warps ===========================
@@ -541,11 +538,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             }
           }
           if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
-          fence_async_smem();
-          tc_fence_before();
-          if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; }
-          step_bar();
-          if (DBG) { t0 = clock64(); tcnt[cls + 3] += t0 - t1; tcnt[cls + 4] += 1; }
+          if (s < NSTAGE - 1) {
+            // hand the slot to the issuer: operands visible to the async proxy, TMEM reads retired
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&misc->ready[slot]);
+          }
+          if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; tcnt[cls + 4] += 1; }
         }
       }
       if (TRAIN && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
