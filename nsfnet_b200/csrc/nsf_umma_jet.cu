@@ -87,6 +87,7 @@ struct Misc {
   uint64_t wbar[2];      // weight image landed in buffer b (TMA complete_tx)
   uint64_t ready[2];     // the slot's operands are written and its previous results consumed (one arrival per epilogue warp)
   uint64_t wfree[2];     // every MMA reading weight buffer b has completed (tcgen05.commit)
+  uint64_t wdone[2];     // the slot's weight-gradient MMAs (readers of its C images) have completed (tcgen05.commit)
   uint32_t tmem_base;
   uint32_t pad[3];
   float ov[2][P][16];    // outputs / output adjoints [slot][p][4*s + o]
@@ -113,9 +114,9 @@ __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, f
 
 __host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t layout_type) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29); }
 
-// ---- issuer: all MMAs of stage s for one slot (executed by the whole issuer warp, see mma_tf32_elect2) ----
+// ---- issuer: the MMAs of stage s for one slot (executed by the whole issuer warp, see mma_tf32_elect2) ----
 template <int L>
-__device__ __forceinline__ void issue_stage(uint32_t smem_base, uint32_t tmem, int s, int slot, int wbuf, bool zero_dw, uint32_t leader) {
+__device__ __forceinline__ void issue_main(uint32_t smem_base, uint32_t tmem, int s, int slot, int wbuf, uint32_t leader) {
   const uint32_t wa = smem_base + (uint32_t)wbuf * WBUF;
   const uint32_t sb = smem_base + OFF_SLOT + (uint32_t)slot * SLOT;
   const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
@@ -140,7 +141,11 @@ __device__ __forceinline__ void issue_stage(uint32_t smem_base, uint32_t tmem, i
       mma_tf32_elect2(d_col, ah0 + da, AHI, bh0 + db, BHI, idesc, 1, leader);
     }
   }
-  if (s > L) {  // wgrad: dW_l[128, 80] += ZC[128, 4P] * AC[80, 4P]^T
+}
+template <int L>
+__device__ __forceinline__ void issue_wgrad(uint32_t smem_base, uint32_t tmem, int s, int slot, bool zero_dw, uint32_t leader) {
+  const uint32_t sb = smem_base + OFF_SLOT + (uint32_t)slot * SLOT;
+  {  // wgrad: dW_l[128, 80] += ZC[128, 4P] * AC[80, 4P]^T
     const int l = 2 * L - s;
     const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
     const uint32_t dw_col = tmem + (uint32_t)((l - 1) * NW);
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
     mbar_init(&misc->ready[0], NEPI / 32); mbar_init(&misc->ready[1], NEPI / 32);
     mbar_init(&misc->wfree[0], 1); mbar_init(&misc->wfree[1], 1);
+    mbar_init(&misc->wdone[0], 1); mbar_init(&misc->wdone[1], 1);
     mbar_fence_init();
   }
   // zero the operand slots once (the M = 128 operand fetch reads 48 rows past the 80 real ones) and the loss sums
@@ -282,9 +288,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           if (slot == 0) { mbar_wait(&misc->wbar[b], (wphases >> b) & 1u); wphases ^= 1u << b; }
           tc_fence_after();
           if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
-          issue_stage<L>(smem_base, tmem, s, slot, (int)b, (pr % FLUSH) == 0 && slot == 0, leader);
+          // dgrad first: the epilogue of the next stage only needs its result; the weight-gradient MMAs get their own
+          // completion barrier (they read the C images, which that epilogue rewrites last)
+          issue_main<L>(smem_base, tmem, s, slot, (int)b, leader);
           mma_commit_elect(&misc->mbar[slot], leader);
           if (slot == 1) mma_commit_elect(&misc->wfree[b], leader);
+          if (s > L) {
+            issue_wgrad<L>(smem_base, tmem, s, slot, (pr % FLUSH) == 0 && slot == 0, leader);
+            mma_commit_elect(&misc->wdone[slot], leader);
+          }
           __syncwarp();
           if (DBG) { t1 = clock64(); icnt[1] += t1 - t0; icnt[4] += 1; }
         }
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     float gb[MAXL];
 #pragma unroll
     for (int i = 0; i < MAXL; ++i) gb[i] = 0.f;
-    uint32_t mphases = 0;                                          // bit slot: parity to wait for on mbar[slot]
+    uint32_t mphases = 0, wdphases = 0;                            // bit slot: parity to wait for on mbar[slot] / wdone[slot]
     const uint32_t d_base = tmem + e.lane_addr + (uint32_t)((L - 1) * NW + e.sub * (4 * PPT));
     const uint32_t slot0 = smem_base + OFF_SLOT;
     long long tcnt[10];      // [fwd | rev] x {MMA wait, work, fence, barrier, steps}
@@ -525,6 +537,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
                 if (l >= 1) {
                   split4(zb, hi, lo);
                   store_R(sb, e, pi, hi, lo);
+                  if (pi == 0) { mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u); }   // C images: their last readers are done
                   store_C(sb + 2 * RB, e, pi, hi, lo);
                   float av[4];
                   act_from_stash(st_lm1[pi], av);
@@ -536,6 +549,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
               }
               gb[l] += sb0;
             }
+            if (l == 0 || !e.active) mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u);   // keeps the parity; precedes flush_dw
+            wdphases ^= 1u << slot;
           }
           if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
           if (s < NSTAGE - 1) {
