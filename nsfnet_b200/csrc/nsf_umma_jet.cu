@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     uint32_t rphases = 0, wphases = 0;     // bit = slot / weight buffer: parity to wait for
     uint32_t stage_ctr = 0;                // MMA stages issued so far (selects the weight buffer)
     long long icnt[5] = {0, 0, 0, 0, 0};   // weight wait, issue, operand wait, -, stage-slots
+    long long swait[2 * MAXL];             // operand wait per stage (diagnostic rows of the two non-epilogue warps)
+#pragma unroll
+    for (int i = 0; i < 2 * MAXL; ++i) swait[i] = 0;
     for (int pr = 0; pr < my_pairs; ++pr) {
 #pragma unroll 1
       for (int s = 1; s < NSTAGE; ++s) {
@@ -284,7 +287,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           long long t0 = 0, t1 = 0;
           if (DBG) t0 = clock64();
           mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u); rphases ^= 1u << slot;
-          if (DBG) { t1 = clock64(); icnt[2] += t1 - t0; t0 = t1; }
+          if (DBG) {
+            t1 = clock64(); icnt[2] += t1 - t0;
+#pragma unroll
+            for (int i = 1; i < 2 * MAXL; ++i) if (i == s) swait[i] += t1 - t0;
+            t0 = t1;
+          }
           if (slot == 0) { mbar_wait(&misc->wbar[b], (wphases >> b) & 1u); wphases ^= 1u << b; }
           tc_fence_after();
           if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     if (DBG && lane == 0) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) a.dbg[((size_t)blockIdx.x * 16 + warp) * 16 + i] = icnt[i];
+#pragma unroll
+      for (int i = 0; i < 2 * MAXL; ++i) a.dbg[((size_t)blockIdx.x * 16 + (ISSUER_WARP + 4)) * 16 + i] = swait[i];
     }
   } else if (warp == ISSUER_WARP + 4) {
     // =========================== weight producer (one lane) ===========================
@@ -353,215 +363,245 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 #pragma unroll
     for (int i = 0; i < 10; ++i) tcnt[i] = 0;
 
-    for (int pr = 0; pr < my_pairs; ++pr) {
-      const long long pair = (long long)blockIdx.x + (long long)pr * gridDim.x;
-      const long long pA = pair * 2 * P;                                    // first point of slot A's tile; slot B follows
-      const long long rem = a.n - pA;
-      const int nvA = (int)(rem < 0 ? 0 : (rem < P ? rem : P)), nvB = (int)(rem - P < 0 ? 0 : (rem - P < P ? rem - P : P));
+    // one (stage, slot) step of this warp's share of a tile; `s` is a literal / unrolled constant at every call site
+    auto stage_step = [&](const int s, const int slot, const long long pA) {
+      const long long rem = a.n - pA - (long long)slot * P;
+      const int nvalid = (int)(rem < 0 ? 0 : (rem < P ? rem : P));
+      const long long p0 = pA + slot * P;
+      const uint32_t sb = slot0 + (uint32_t)slot * SLOT;
+      float4* st_slot = TRAIN ? stash_thr + (size_t)slot * (L * P * KP) : nullptr;
+      const uint32_t d_addr = d_base + (uint32_t)(slot * NCOL);
+      // reverse stages: fetch the stashed pre-activations (L2) BEFORE waiting for the MMAs of this stage
+      const bool is_rev = TRAIN && s >= L;
+      const int lrev = 2 * L - s - 1;                                   // layer whose tanh is differentiated (s = L: L-1)
+      float4 st_l[PPT], st_lm1[PPT];
+      if (is_rev && e.active) {
 #pragma unroll
-      for (int s = 0; s < NSTAGE; ++s) {
-#pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
-          const long long p0 = pA + slot * P;
-          const int nvalid = slot ? nvB : nvA;
-          const uint32_t sb = slot0 + (uint32_t)slot * SLOT;
-          float4* st_slot = TRAIN ? stash_thr + (size_t)slot * (L * P * KP) : nullptr;
-          const uint32_t d_addr = d_base + (uint32_t)(slot * NCOL);
-          // reverse stages: fetch the stashed pre-activations (L2) BEFORE waiting for the MMAs of this stage
-          const bool is_rev = TRAIN && s >= L;
-          const int lrev = 2 * L - s - 1;                                   // layer whose tanh is differentiated (s = L: L-1)
-          float4 st_l[PPT], st_lm1[PPT];
-          if (is_rev && e.active) {
-#pragma unroll
-            for (int pi = 0; pi < PPT; ++pi) {
-              st_l[pi] = __ldcs(st_slot + lrev * (P * KP) + pi * KP);
-              if (lrev >= 1) st_lm1[pi] = __ldcs(st_slot + (lrev - 1) * (P * KP) + pi * KP);
-            }
-          }
-          float xv[PPT], yv[PPT];
-          if (s == 0 || (TRAIN && s == 2 * L - 1)) {
-#pragma unroll
-            for (int pi = 0; pi < PPT; ++pi) {
-              const int p = e.sub * PPT + pi;
-              xv[pi] = p < nvalid ? __ldg(a.x + p0 + p) : 0.f;
-              yv[pi] = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
-            }
-          }
-          const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
-          long long t0 = 0, t1 = 0;
-          if (DBG) t0 = clock64();
-          if (s >= 1) {
-            mbar_wait(&misc->mbar[slot], (mphases >> slot) & 1u);
-            mphases ^= 1u << slot;
-            tc_fence_after();
-          }
-          if (DBG) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
-
-          if (s == 0) {
-            // ---- layer 0 (K = 2) -------------------------------------------------------------
-            if (e.active) {
-#pragma unroll
-              for (int pi = 0; pi < PPT; ++pi) {
-                const float z[4] = {fmaf(w0x, xv[pi], fmaf(w0y, yv[pi], b0)), w0x, w0y, 0.f};
-                float v[4], hi[4], lo[4];
-                jet_fwd(z, v);
-                if (TRAIN) __stcs(st_slot + pi * KP, make_float4(v[0], z[1], z[2], z[3]));
-                split4(v, hi, lo);
-                store_R(sb, e, pi, hi, lo);
-              }
-            }
-          } else if (s < L) {
-            // ---- hidden layer s forward --------------------------------------------------------
-            float z[PPT][4];
-            tmem_ld8(d_addr, &z[0][0]);
-            tmem_ld_wait();
-            if (e.active) {
-#pragma unroll
-              for (int pi = 0; pi < PPT; ++pi) {
-                z[pi][0] += bias[s];
-                float v[4], hi[4], lo[4];
-                jet_fwd(z[pi], v);
-                if (TRAIN) __stcs(st_slot + s * (P * KP) + pi * KP, make_float4(v[0], z[pi][1], z[pi][2], z[pi][3]));
-                split4(v, hi, lo);
-                store_R(sb, e, pi, hi, lo);
-              }
-            }
-          } else if (s == L) {
-            // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
-            float o[PPT][4];
-            tmem_ld8(d_addr, &o[0][0]);
-            tmem_ld_wait();
-            if (e.q == 0 && lane < 3) {
-#pragma unroll
-              for (int pi = 0; pi < PPT; ++pi) {
-                const int p = e.sub * PPT + pi;
-                misc->ov[slot][p][0 * 4 + lane] = o[pi][0] + bo;
-                misc->ov[slot][p][1 * 4 + lane] = o[pi][1];
-                misc->ov[slot][p][2 * 4 + lane] = o[pi][2];
-                misc->ov[slot][p][3 * 4 + lane] = o[pi][3];
-              }
-            }
-            epi_bar();
-            if (tid < P) {
-              const int p = tid;
-              const bool ok = p < nvalid;
-              const long long gp = p0 + p;
-              float* ov = misc->ov[slot][p];
-              float* red = misc->red[p];
-              const float u = ov[0], v = ov[1];
-              const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
-              const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
-              const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
-              float ee = 0.f, vis = 0.f;
-              if (a.has_evm) {
-                ee = ok ? __ldg(a.e_in + gp) : 0.f;
-                vis = a.vis_t0;
-                if (a.vtm_in && ok) vis = fminf(a.vis_t0, __ldg(a.vtm_in + gp));
-              }
-              const float nu = a.inv_Re + vis;
-              const float eq1 = (u * ux + v * uy) + px - nu * ul;
-              const float eq2 = (u * vx + v * vy) + py - nu * vl;
-              const float eq3 = ux + vy;
-              const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
-              const float w = (a.w && ok) ? __ldg(a.w + gp) : 1.f;
-              if (ok) {
-                red[0] += w * eq1 * eq1; red[1] += w * eq2 * eq2; red[2] += w * eq3 * eq3; red[3] += w * eq4 * eq4;
-                red[4] += vis; red[5] += 1.f;
-                if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
-                if (a.vis_t_out) a.vis_t_out[gp] = vis;
-                if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
-              }
-              if (TRAIN) {
-                const float cw = ok ? a.c_eq * w : 0.f;
-                const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
-                const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
-                const float g3 = 2.f * cw * eq3;
-                const float g4 = a.k4 * cw * eq4;
-                ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
-                ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
-                ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
-                ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
-                red[6] += ov[0]; red[7] += ov[1]; red[8] += ov[2];
-                if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
-              }
-            }
-            if (TRAIN) {
-              epi_bar();
-              if (e.active) {
-                float sb0 = 0.f;
-#pragma unroll
-                for (int pi = 0; pi < PPT; ++pi) {
-                  const float4* ov4 = reinterpret_cast<const float4*>(misc->ov[slot][e.sub * PPT + pi]);
-                  float ab[4], zb[4], act[4], hi[4], lo[4];
-                  float4 ovs[4];
-#pragma unroll
-                  for (int st = 0; st < 4; ++st) {
-                    ovs[st] = ov4[st];
-                    ab[st] = fmaf(ovs[st].x, wl0, fmaf(ovs[st].y, wl1, ovs[st].z * wl2));
-                  }
-                  zbar_from(st_l[pi], ab, zb);
-                  act_from_stash(st_l[pi], act);
-#pragma unroll
-                  for (int st = 0; st < 4; ++st) {
-                    gwl[0] = fmaf(ovs[st].x, act[st], gwl[0]);
-                    gwl[1] = fmaf(ovs[st].y, act[st], gwl[1]);
-                    gwl[2] = fmaf(ovs[st].z, act[st], gwl[2]);
-                  }
-                  sb0 += zb[0];
-                  if (L >= 2) {
-                    split4(zb, hi, lo);
-                    store_R(sb, e, pi, hi, lo);
-                    store_C(sb + 2 * RB, e, pi, hi, lo);
-                    float av[4];
-                    act_from_stash(st_lm1[pi], av);
-                    split4(av, hi, lo);
-                    store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
-                  }
-                }
-                gb[L - 1] += sb0;
-              }
-            }
-          } else {
-            // ---- reverse: D holds the adjoint of layer l's activations, l = 2L - s - 1 ------------------
-            const int l = (2 * L - s - 1) >= 0 ? (2 * L - s - 1) : 0;
-            float ab[PPT][4];
-            tmem_ld8(d_addr, &ab[0][0]);
-            tmem_ld_wait();
-            if (e.active) {
-              float sb0 = 0.f;
-#pragma unroll
-              for (int pi = 0; pi < PPT; ++pi) {
-                float zb[4], hi[4], lo[4];
-                zbar_from(st_l[pi], ab[pi], zb);
-                sb0 += zb[0];
-                if (l >= 1) {
-                  split4(zb, hi, lo);
-                  store_R(sb, e, pi, hi, lo);
-                  if (pi == 0) { mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u); }   // C images: their last readers are done
-                  store_C(sb + 2 * RB, e, pi, hi, lo);
-                  float av[4];
-                  act_from_stash(st_lm1[pi], av);
-                  split4(av, hi, lo);
-                  store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
-                } else {
-                  gw0x += fmaf(zb[0], xv[pi], zb[1]); gw0y += fmaf(zb[0], yv[pi], zb[2]);
-                }
-              }
-              gb[l] += sb0;
-            }
-            if (l == 0 || !e.active) mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u);   // keeps the parity; precedes flush_dw
-            wdphases ^= 1u << slot;
-          }
-          if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
-          if (s < NSTAGE - 1) {
-            // hand the slot to the issuer: operands visible to the async proxy, TMEM reads retired
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&misc->ready[slot]);
-          }
-          if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; tcnt[cls + 4] += 1; }
+        for (int pi = 0; pi < PPT; ++pi) {
+          st_l[pi] = __ldcs(st_slot + lrev * (P * KP) + pi * KP);
+          if (lrev >= 1) st_lm1[pi] = __ldcs(st_slot + (lrev - 1) * (P * KP) + pi * KP);
         }
+      }
+      float4 stv[PPT];                                                  // (t, zx, zy, z_lap) of a forward stage, stashed after the hand-over
+      float xv[PPT], yv[PPT];
+      if (s == 0 || (TRAIN && s == 2 * L - 1)) {
+#pragma unroll
+        for (int pi = 0; pi < PPT; ++pi) {
+          const int p = e.sub * PPT + pi;
+          xv[pi] = p < nvalid ? __ldg(a.x + p0 + p) : 0.f;
+          yv[pi] = p < nvalid ? __ldg(a.y + p0 + p) : 0.f;
+        }
+      }
+      // output stage: the residual threads' per-point inputs come from L2 as well; and the C image of a^{L-2} depends
+      // on the stash only (its last readers finished with the previous tile), so it is written before the wait
+      float pre_e = 0.f, pre_vtm = 0.f, pre_w = 1.f;
+      if (s == L) {
+        if (tid < P && tid < nvalid) {
+          const long long gp = p0 + tid;
+          if (a.has_evm) { pre_e = __ldg(a.e_in + gp); pre_vtm = a.vtm_in ? __ldg(a.vtm_in + gp) : a.vis_t0; }
+          if (a.w) pre_w = __ldg(a.w + gp);
+        }
+        if (TRAIN && L >= 2 && e.active) {
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            float av[4], hi[4], lo[4];
+            act_from_stash(st_lm1[pi], av);
+            split4(av, hi, lo);
+            store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
+          }
+        }
+      }
+      const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
+      long long t0 = 0, t1 = 0;
+      if (DBG) t0 = clock64();
+      if (s >= 1) {
+        mbar_wait(&misc->mbar[slot], (mphases >> slot) & 1u);
+        mphases ^= 1u << slot;
+        tc_fence_after();
+      }
+      if (DBG) { t1 = clock64(); tcnt[cls + 0] += t1 - t0; }
+
+      if (s == 0) {
+        // ---- layer 0 (K = 2) -------------------------------------------------------------
+        if (e.active) {
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            const float z[4] = {fmaf(w0x, xv[pi], fmaf(w0y, yv[pi], b0)), w0x, w0y, 0.f};
+            float v[4], hi[4], lo[4];
+            jet_fwd(z, v);
+            stv[pi] = make_float4(v[0], z[1], z[2], z[3]);
+            split4(v, hi, lo);
+            store_R(sb, e, pi, hi, lo);
+          }
+        }
+      } else if (s < L) {
+        // ---- hidden layer s forward --------------------------------------------------------
+        float z[PPT][4];
+        tmem_ld8(d_addr, &z[0][0]);
+        tmem_ld_wait();
+        if (e.active) {
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            z[pi][0] += bias[s];
+            float v[4], hi[4], lo[4];
+            jet_fwd(z[pi], v);
+            stv[pi] = make_float4(v[0], z[pi][1], z[pi][2], z[pi][3]);
+            split4(v, hi, lo);
+            store_R(sb, e, pi, hi, lo);
+          }
+        }
+      } else if (s == L) {
+        // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
+        float o[PPT][4];
+        tmem_ld8(d_addr, &o[0][0]);
+        tmem_ld_wait();
+        if (e.q == 0 && lane < 3) {
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            const int p = e.sub * PPT + pi;
+            misc->ov[slot][p][0 * 4 + lane] = o[pi][0] + bo;
+            misc->ov[slot][p][1 * 4 + lane] = o[pi][1];
+            misc->ov[slot][p][2 * 4 + lane] = o[pi][2];
+            misc->ov[slot][p][3 * 4 + lane] = o[pi][3];
+          }
+        }
+        epi_bar();
+        if (tid < P) {
+          const int p = tid;
+          const bool ok = p < nvalid;
+          const long long gp = p0 + p;
+          float* ov = misc->ov[slot][p];
+          float* red = misc->red[p];
+          const float u = ov[0], v = ov[1];
+          const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
+          const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
+          const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
+          float ee = 0.f, vis = 0.f;
+          if (a.has_evm) {
+            ee = pre_e;
+            vis = ok ? fminf(a.vis_t0, pre_vtm) : a.vis_t0;
+          }
+          const float nu = a.inv_Re + vis;
+          const float eq1 = (u * ux + v * uy) + px - nu * ul;
+          const float eq2 = (u * vx + v * vy) + py - nu * vl;
+          const float eq3 = ux + vy;
+          const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
+          const float w = pre_w;
+          if (ok) {
+            red[0] += w * eq1 * eq1; red[1] += w * eq2 * eq2; red[2] += w * eq3 * eq3; red[3] += w * eq4 * eq4;
+            red[4] += vis; red[5] += 1.f;
+            if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
+            if (a.vis_t_out) a.vis_t_out[gp] = vis;
+            if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
+          }
+          if (TRAIN) {
+            const float cw = ok ? a.c_eq * w : 0.f;
+            const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
+            const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
+            const float g3 = 2.f * cw * eq3;
+            const float g4 = a.k4 * cw * eq4;
+            ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
+            ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
+            ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
+            ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
+            red[6] += ov[0]; red[7] += ov[1]; red[8] += ov[2];
+            if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
+          }
+        }
+        if (TRAIN) {
+          epi_bar();
+          if (e.active) {
+            float sb0 = 0.f;
+#pragma unroll
+            for (int pi = 0; pi < PPT; ++pi) {
+              const float4* ov4 = reinterpret_cast<const float4*>(misc->ov[slot][e.sub * PPT + pi]);
+              float ab[4], zb[4], act[4], hi[4], lo[4];
+              float4 ovs[4];
+#pragma unroll
+              for (int st = 0; st < 4; ++st) {
+                ovs[st] = ov4[st];
+                ab[st] = fmaf(ovs[st].x, wl0, fmaf(ovs[st].y, wl1, ovs[st].z * wl2));
+              }
+              zbar_from(st_l[pi], ab, zb);
+              act_from_stash(st_l[pi], act);
+#pragma unroll
+              for (int st = 0; st < 4; ++st) {
+                gwl[0] = fmaf(ovs[st].x, act[st], gwl[0]);
+                gwl[1] = fmaf(ovs[st].y, act[st], gwl[1]);
+                gwl[2] = fmaf(ovs[st].z, act[st], gwl[2]);
+              }
+              sb0 += zb[0];
+              if (L >= 2) {
+                split4(zb, hi, lo);
+                store_R(sb, e, pi, hi, lo);
+                store_C(sb + 2 * RB, e, pi, hi, lo);
+              }
+            }
+            gb[L - 1] += sb0;
+          }
+        }
+      } else {
+        // ---- reverse: D holds the adjoint of layer l's activations, l = 2L - s - 1 ------------------
+        const int l = (2 * L - s - 1) >= 0 ? (2 * L - s - 1) : 0;
+        float ab[PPT][4];
+        tmem_ld8(d_addr, &ab[0][0]);
+        tmem_ld_wait();
+        if (e.active) {
+          float sb0 = 0.f;
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) {
+            float zb[4], hi[4], lo[4];
+            zbar_from(st_l[pi], ab[pi], zb);
+            sb0 += zb[0];
+            if (l >= 1) {
+              split4(zb, hi, lo);
+              store_R(sb, e, pi, hi, lo);
+              if (pi == 0) { mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u); }   // C images: their last readers are done
+              store_C(sb + 2 * RB, e, pi, hi, lo);
+              float av[4];
+              act_from_stash(st_lm1[pi], av);
+              split4(av, hi, lo);
+              store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
+            } else {
+              gw0x += fmaf(zb[0], xv[pi], zb[1]); gw0y += fmaf(zb[0], yv[pi], zb[2]);
+            }
+          }
+          gb[l] += sb0;
+        }
+        if (l == 0 || !e.active) mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u);   // keeps the parity; precedes flush_dw
+        wdphases ^= 1u << slot;
+      }
+      if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
+      if (s < NSTAGE - 1) {
+        // hand the slot to the issuer: operands visible to the async proxy, TMEM reads retired
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&misc->ready[slot]);
+      }
+      if (TRAIN && s < L && e.active) {
+        // the stash stores go to L2 after the hand-over: the proxy fence above would wait for them
+#pragma unroll
+        for (int pi = 0; pi < PPT; ++pi) __stcs(st_slot + s * (P * KP) + pi * KP, stv[pi]);
+      }
+      if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; tcnt[cls + 4] += 1; }
+    };
+
+    const long long pair_stride = (long long)gridDim.x * 2 * P;
+    long long pA = (long long)blockIdx.x * 2 * P;                         // first point of slot A's tile; slot B follows
+    if (my_pairs > 0) { stage_step(0, 0, pA); stage_step(0, 1, pA); }
+    for (int pr = 0; pr < my_pairs; ++pr, pA += pair_stride) {
+#pragma unroll
+      for (int s = 1; s < NSTAGE - 1; ++s) {
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) stage_step(s, slot, pA);
+      }
+      // last stage of this pair fused with stage 0 of the next pair, slot by slot: the issuer gets slot A's first
+      // operands of the next tile while slot B still finishes, so the tensor pipe does not drain between pairs
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        stage_step(NSTAGE - 1, slot, pA);
+        if (pr + 1 < my_pairs) stage_step(0, slot, pA + pair_stride);
       }
       if (TRAIN && ((pr + 1) % FLUSH == 0 || pr == my_pairs - 1)) {
         // every MMA of this pair has completed (its barriers were waited on above); the next pair's first
