@@ -14,8 +14,8 @@
 //   warp 11                               : spare (quadrant 3 holds only padding rows)
 // Two point tiles ("slots" A, B; P = 8 points each) are in flight: while the tensor pipe runs the MMAs of
 // one slot, the epilogue warps work on the other slot.  There is no CTA-wide barrier in the steady state: the
-// warps are coupled by mbarriers only (ready: epilogue -> issuer, mbar: MMAs done -> epilogue, wbar / wfree:
-// weight buffer full / free), so the issuer queues the next slot's MMAs while the previous ones still execute.
+// warps are coupled by mbarriers only (ready: epilogue -> issuer, mbar: MMAs done -> epilogue,
+// weights landed -> counted on slot A's ready barrier, wfree: weight buffer free), so the issuer queues the next slot's MMAs while the previous ones still execute.
 //
 // Per tile the stages are  s = 0: layer 0 (K = 2, FFMA);  s = 1..L-1: hidden layer s (fwd MMA);  s = L:
 // output layer (MMA, M = 64) + residuals + adjoint seeds;  s = L+1..2L-1: reverse of hidden layer l = 2L-s
@@ -84,8 +84,10 @@ struct UArgs {
 
 struct Misc {
   uint64_t mbar[2];      // "done": the slot's MMAs have completed (tcgen05.commit)
-  uint64_t wbar[2];      // weight image landed in buffer b (TMA complete_tx)
-  uint64_t ready[2];     // the slot's operands are written and its previous results consumed (one arrival per epilogue warp)
+  uint64_t wbar[2];      // (diagnostics only)
+  uint64_t ready[2];     // the slot's operands are written and its previous results consumed (one arrival per epilogue warp);
+                         // ready[0] also carries the stage's weight image (producer arrival + TMA complete_tx): every
+                         // mbarrier poll costs 200+ cycles while the MMAs saturate shared memory, so the issuer polls once
   uint64_t wfree[2];     // every MMA reading weight buffer b has completed (tcgen05.commit)
   uint64_t wdone[2];     // the slot's weight-gradient MMAs (readers of its C images) have completed (tcgen05.commit)
   uint32_t tmem_base;
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     if (smem_base & 1023u) __trap();                // the swizzled R images assume a 1 KB aligned window
     mbar_init(&misc->mbar[0], 1); mbar_init(&misc->mbar[1], 1);
     mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
-    mbar_init(&misc->ready[0], NEPI / 32); mbar_init(&misc->ready[1], NEPI / 32);
+    mbar_init(&misc->ready[0], NEPI / 32 + 1); mbar_init(&misc->ready[1], NEPI / 32);
     mbar_init(&misc->wfree[0], 1); mbar_init(&misc->wfree[1], 1);
     mbar_init(&misc->wdone[0], 1); mbar_init(&misc->wdone[1], 1);
     mbar_fence_init();
@@ -272,9 +274,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     // drains between stages.  The whole warp walks the loop convergently with warp-uniform state; one elected lane
     // issues the MMAs and the commits.
     const uint32_t leader = elect_one();
-    uint32_t rphases = 0, wphases = 0;     // bit = slot / weight buffer: parity to wait for
+    uint32_t rphases = 0;                  // bit = slot: parity to wait for
     uint32_t stage_ctr = 0;                // MMA stages issued so far (selects the weight buffer)
-    long long icnt[5] = {0, 0, 0, 0, 0};   // weight wait, issue, operand wait, -, stage-slots
+    long long icnt[5] = {0, 0, 0, 0, 0};   // -, issue, operand (+ weight) wait, -, stage-slots
     long long swait[2 * MAXL];             // operand wait per stage (diagnostic rows of the two non-epilogue warps)
 #pragma unroll
     for (int i = 0; i < 2 * MAXL; ++i) swait[i] = 0;
@@ -293,7 +295,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             for (int i = 1; i < 2 * MAXL; ++i) if (i == s) swait[i] += t1 - t0;
             t0 = t1;
           }
-          if (slot == 0) { mbar_wait(&misc->wbar[b], (wphases >> b) & 1u); wphases ^= 1u << b; }
           tc_fence_after();
           if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
           // dgrad first: the epilogue of the next stage only needs its result; the weight-gradient MMAs get their own
@@ -326,8 +327,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       for (long long i = 0; i < total; ++i) {
         const int b = (int)(i & 1);
         if (i >= 2) mbar_wait(&misc->wfree[b], (uint32_t)(((i >> 1) - 1) & 1));
-        mbar_expect_tx(&misc->wbar[b], WBUF);
-        tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->wbar[b]);
+        // the image is accounted on slot A's `ready` barrier of ITS stage: wait until the previous stage's phase is over
+        if (i >= 1) mbar_wait(&misc->ready[0], (uint32_t)((i - 1) & 1));
+        mbar_expect_tx(&misc->ready[0], WBUF);
+        tma_bulk_g2s(smem + (size_t)b * WBUF, a.wimg + (size_t)img * WBUF, WBUF, &misc->ready[0]);
         if (++img == NSTAGE - 1) img = 0;
       }
     }
