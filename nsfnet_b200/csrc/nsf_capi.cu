@@ -108,6 +108,9 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
 #ifndef NSF_EMU
   nsf_umma_free(ctx);
   nsf_umma2_free(ctx);
+  if (ctx->side) cudaStreamDestroy((cudaStream_t)ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
   if (ctx->ev0) cudaEventDestroy((cudaEvent_t)ctx->ev0);
   if (ctx->ev1) cudaEventDestroy((cudaEvent_t)ctx->ev1);
 #endif
@@ -246,6 +249,27 @@ static void phys_args(NsfKernelArgs& a, const NsfPhysics* ph, long long n) {
   a.has_evm = has_evm ? 1 : 0;
 }
 
+// e = net_1(x, y) at n points: the thread-per-point kernel when it covers the net, else the FFMA tile kernel (needs ctx->evm.pk packed)
+static int evm_forward(NsfCtx* ctx, const float* params_evm, bool packed, const float* x, const float* y, long long n, float* out, nsf_stream_t st) {
+#ifndef NSF_EMU
+  if (nsf_value_fwd_supported(ctx->evm.g)) {
+    NSF_TRY(nsf_value_fwd_launch(ctx->evm.g, ctx->sms, params_evm, x, y, n, out, st)); ctx->launches++;
+    return NSF_OK;
+  }
+#endif
+  if (!packed) { NSF_TRY(nsf_pack_launch(ctx->evm.g, params_evm, ctx->evm.pk, st)); ctx->launches++; }
+  NsfKernelArgs f;
+  f = NsfKernelArgs();
+  f.g = ctx->evm.g; f.pk = ctx->evm.pk; f.x = x; f.y = y; f.n = n; f.mode = NSF_MODE_FWD;
+  f.out = out; f.scratch = nullptr; f.stash = nullptr;
+  const int pt = nsf_ffma_pt(1, ctx->evm.g.HP);
+  const long long tiles = (n + pt - 1) / pt;
+  long long cap = (long long)ctx->sms * nsf_ffma_occupancy(1, ctx->evm.g.HP);
+  if (cap > ctx->evm.rows) cap = ctx->evm.rows;
+  NSF_TRY(nsf_ffma_launch(f, 1, (int)(tiles < cap ? tiles : cap), st)); ctx->launches++;
+  return NSF_OK;
+}
+
 static int valid_ptr(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 extern "C" int nsf_forward(NsfCtx* ctx, int32_t which, const float* params, const float* x, const float* y, int64_t n,
@@ -257,6 +281,7 @@ extern "C" int nsf_forward(NsfCtx* ctx, int32_t which, const float* params, cons
   nsf_stream_t st = (nsf_stream_t)stream;
   NsfNetState& s = which ? ctx->evm : ctx->main;
   ctx->launches = 0;
+  if (which == 1) return n == 0 ? NSF_OK : evm_forward(ctx, params, false, x, y, n, out, st);
   NSF_TRY(nsf_pack_launch(s.g, params, s.pk, st)); ctx->launches++;
   if (n == 0) return NSF_OK;
   NsfKernelArgs a;
@@ -280,13 +305,9 @@ extern "C" int nsf_residuals(NsfCtx* ctx, const float* params_main, const float*
   if (n == 0) return NSF_OK;
   const float* e_ptr = nullptr;
   if (has_evm) {
-    NSF_TRY(nsf_pack_launch(ctx->evm.g, params_evm, ctx->evm.pk, st)); ctx->launches++;
     float* eb = e_out;
     if (!eb) { NSF_TRY(ensure_cap(ctx, n)); eb = ctx->e_buf; }
-    NsfKernelArgs f;
-    base_args(f, ctx->evm, x, y, n, NSF_MODE_FWD);
-    f.out = eb; f.scratch = nullptr; f.stash = nullptr;
-    NSF_TRY(nsf_ffma_launch(f, 1, grid_for(ctx, ctx->evm, 1, n), st)); ctx->launches++;
+    NSF_TRY(evm_forward(ctx, params_evm, false, x, y, n, eb, st));
     e_ptr = eb;
   }
   NsfKernelArgs a;
@@ -324,6 +345,7 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   ctx->launches = 0;
   NSF_TRY(nsf_pack_launch(M.g, params_main, M.pk, st)); ctx->launches++;
 
+
   // grids of the launches that accumulate into the main net's gradient rows
   int grids[1 + NSF_MAX_BLOCKS];
   grids[0] = n_f > 0 ? grid_for(ctx, M, 4, n_f) : 0;
@@ -339,32 +361,86 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   }
 #endif
   for (int b = 0; b < n_blocks; ++b) grids[1 + b] = blocks[b].n > 0 ? grid_for(ctx, M, 1, blocks[b].n) : 0;
+  // With the tcgen05 jet kernel (own activation stash, one gradient row per SM) the data blocks get the gradient rows
+  // BEHIND the jet kernel's and run on a side stream beside the EVM forward and the jet kernel; otherwise every launch
+  // accumulates into the same rows, in stream order.
+  int blk_rows = 0, blk_first = -1;
+  for (int b = 0; b < n_blocks; ++b) {
+    if (grids[1 + b] > 0 && blk_first < 0) blk_first = b;
+    if (grids[1 + b] > blk_rows) blk_rows = grids[1 + b];
+  }
+  bool side = false;
+#ifndef NSF_EMU
+  side = n_f > 0 && effective_path(ctx) == 2 && blk_rows > 0 && grids[0] + blk_rows <= M.rows;
+  if (side && !ctx->side) {
+    cudaStream_t s2; cudaEvent_t e0, e1;
+    NSF_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    NSF_CUDA_OK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    NSF_CUDA_OK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    ctx->side = s2; ctx->ev_fork = e0; ctx->ev_join = e1;
+  }
+#endif
   int first = -1, rows_used = 0;
   for (int i = 0; i < 1 + n_blocks; ++i) {
     if (grids[i] > 0 && first < 0) first = i;
     if (grids[i] > rows_used) rows_used = grids[i];
   }
+  if (side) rows_used = grids[0] + blk_rows;
   if (first < 0) {  // nothing to do: zero outputs
     NSF_RT_OK(nsf_rt_memset0(grad_main, sizeof(float) * M.g.n_params, st));
     NSF_RT_OK(nsf_rt_memset0(loss_parts, sizeof(float) * NSF_LOSS_SLOTS, st));
     if (evm_train) NSF_RT_OK(nsf_rt_memset0(grad_evm, sizeof(float) * ctx->evm.g.n_params, st));
     return NSF_OK;
   }
-  if (rows_used > grids[first]) {  // rows the first (overwriting) launch does not touch
+  if (!side && rows_used > grids[first]) {  // rows the first (overwriting) launch does not touch
     NSF_RT_OK(nsf_rt_memset0(M.scratch + (size_t)grids[first] * M.g.gs_row(), sizeof(float) * (size_t)(rows_used - grids[first]) * M.g.gs_row(), st));
     ctx->launches++;
   }
 
+  // the data blocks (boundary / supervised MSE): value-stream forward + reverse of the main net on a few thousand points
+  auto launch_blocks = [&](nsf_stream_t bst) -> int {
+#ifndef NSF_EMU
+    if (side) {
+      NSF_CUDA_OK(cudaStreamWaitEvent(bst, (cudaEvent_t)ctx->ev_fork, 0));
+      if (blk_rows > grids[1 + blk_first]) {   // rows of the block region that the first (overwriting) block does not touch
+        NSF_RT_OK(nsf_rt_memset0(M.scratch + (size_t)(grids[0] + grids[1 + blk_first]) * M.g.gs_row(),
+                                 sizeof(float) * (size_t)(blk_rows - grids[1 + blk_first]) * M.g.gs_row(), bst));
+        ctx->launches++;
+      }
+    }
+#endif
+    for (int b = 0; b < n_blocks; ++b) {
+      const NsfDataBlock& k = blocks[b];
+      if (k.n <= 0) continue;
+      NsfKernelArgs a;
+      base_args(a, M, k.x, k.y, k.n, NSF_MODE_MSE_STEP);
+      a.accumulate = side ? (b == blk_first ? 0 : 1) : ((first == 1 + b) ? 0 : 1);
+      if (side) a.scratch = M.scratch + (size_t)grids[0] * M.g.gs_row();
+      a.tu = k.u; a.tv = k.v; a.tp = k.p; a.cu = k.cu; a.cv = k.cv; a.cp = k.cp;
+      a.loss_slot = 6 + 4 * b;
+      NSF_TRY(nsf_ffma_launch(a, 1, grids[1 + b], bst)); ctx->launches++;
+    }
+#ifndef NSF_EMU
+    if (side) NSF_CUDA_OK(cudaEventRecord((cudaEvent_t)ctx->ev_join, bst));
+#endif
+    return NSF_OK;
+  };
+#ifndef NSF_EMU
+  if (side) {
+    // fork: the blocks only need the packed image; they overlap the EVM forward and are joined before the persistent
+    // jet kernel starts (its CTAs need whole SMs: leftover block CTAs would delay them)
+    NSF_CUDA_OK(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
+    NSF_TRY(launch_blocks((cudaStream_t)ctx->side));
+  }
+#endif
+
   if (n_f > 0) {
     const float* e_ptr = nullptr;
     if (has_evm) {
-      NSF_TRY(nsf_pack_launch(ctx->evm.g, params_evm, ctx->evm.pk, st)); ctx->launches++;
+      if (evm_train) { NSF_TRY(nsf_pack_launch(ctx->evm.g, params_evm, ctx->evm.pk, st)); ctx->launches++; }   // the reverse pass reads the packed image
       NSF_TRY(ensure_cap(ctx, n_f));
       float* eb = e_out ? e_out : ctx->e_buf;
-      NsfKernelArgs f;
-      base_args(f, ctx->evm, x, y, n_f, NSF_MODE_FWD);
-      f.out = eb; f.scratch = nullptr; f.stash = nullptr;
-      NSF_TRY(nsf_ffma_launch(f, 1, grid_for(ctx, ctx->evm, 1, n_f), st)); ctx->launches++;
+      NSF_TRY(evm_forward(ctx, params_evm, evm_train, x, y, n_f, eb, st));
       e_ptr = eb;
     }
     NsfKernelArgs a;
@@ -374,20 +450,14 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     a.e_in = e_ptr; a.vtm_in = vtm_in; a.vtm_out = vtm_out; a.w = w;
     a.resid_out = residuals_out; a.vis_t_out = vis_t_out;
     a.ebar_out = evm_train ? ctx->ebar_buf : nullptr;
+#ifndef NSF_EMU
+    if (side) NSF_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
+#endif
     NSF_TRY(time_mark(ctx, 0, st));
     NSF_TRY(launch_jet(ctx, a, params_main, &grids[0], st));
     NSF_TRY(time_mark(ctx, 1, st));
   }
-  for (int b = 0; b < n_blocks; ++b) {
-    const NsfDataBlock& k = blocks[b];
-    if (k.n <= 0) continue;
-    NsfKernelArgs a;
-    base_args(a, M, k.x, k.y, k.n, NSF_MODE_MSE_STEP);
-    a.accumulate = (first == 1 + b) ? 0 : 1;
-    a.tu = k.u; a.tv = k.v; a.tp = k.p; a.cu = k.cu; a.cv = k.cv; a.cp = k.cp;
-    a.loss_slot = 6 + 4 * b;
-    NSF_TRY(nsf_ffma_launch(a, 1, grids[1 + b], st)); ctx->launches++;
-  }
+  if (!side) { NSF_TRY(launch_blocks(st)); }
   NSF_TRY(nsf_finalize_launch(M.g, M.scratch, rows_used, M.map, grad_main, loss_parts, st)); ctx->launches++;
 
   if (evm_train) {

@@ -63,6 +63,9 @@ struct NsfCtx {
   void* umma = nullptr;  // tcgen05 path state, tile-major kernel (nsf_umma_jet.cu)
   void* umma2 = nullptr; // tcgen05 path state, layer-major kernel (nsf_umma_jet2.cu)
   int umma2_nt = 0;      // tiles per super-batch of the layer-major kernel (0 = default)
+  void* side = nullptr;     // side stream: the data blocks (boundary / supervised MSE) run beside the EVM forward + jet kernel
+  void* ev_fork = nullptr;
+  void* ev_join = nullptr;
   int timing = 0;        // bracket the dominant kernel with events (nsf_set_timing)
   void* ev0 = nullptr;
   void* ev1 = nullptr;
@@ -81,6 +84,11 @@ int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, con
                         float* loss_parts, nsf_stream_t st);
 int nsf_adam_launch(float* params, const float* grad, float* m, float* v, long long n, float lr, float b1, float b2,
                     float eps, float bc1, float bc2, float grad_scale, nsf_stream_t st);
+
+// nsf_value_fwd.cu (CUDA build only): one-output value forward, thread per point ----------------------------------
+int nsf_value_fwd_supported(const NsfNetGeom& g);
+int nsf_value_fwd_launch(const NsfNetGeom& g, int sms, const float* flat, const float* x, const float* y, long long n, float* out,
+                         nsf_stream_t st);
 
 // nsf_umma_jet.cu (CUDA build only) ---------------------------------------------------------------
 int nsf_umma_supported(const NsfNetGeom& g);
