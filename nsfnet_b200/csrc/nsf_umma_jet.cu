@@ -58,9 +58,7 @@ constexpr uint32_t IMG = (KP / 8) * W_SBO;      // 25600: one weight image (hi o
 constexpr uint32_t WBUF = 2 * IMG;              // hi | lo
 constexpr uint32_t R_ATOM = 512;                // 4 neurons x 128 B (32 columns n) of an R image
 constexpr uint32_t RB = (KP / 4) * R_ATOM;      // 10240: one R image
-constexpr uint32_t C_SP = (KP / 8) * 128;       // 1280: point block of a C image
-constexpr uint32_t CB = P * C_SP;               // 10240: one C image
-constexpr uint32_t SLOT = 2 * RB + 4 * CB;      // 61440: R hi, R lo, ZC hi, ZC lo, AC hi, AC lo
+constexpr uint32_t SLOT = 4 * RB;                // 40960: R hi, R lo (z-bar or activations), RA hi, RA lo (activations of the layer below)
 constexpr uint32_t OFF_SLOT = 2 * WBUF;         // 102400
 constexpr uint32_t OFF_MISC = OFF_SLOT + 2 * SLOT;   // 225280
 constexpr uint32_t MISC = 1536;
@@ -147,20 +145,21 @@ __device__ __forceinline__ void issue_main(uint32_t smem_base, uint32_t tmem, in
 template <int L>
 __device__ __forceinline__ void issue_wgrad(uint32_t smem_base, uint32_t tmem, int s, int slot, bool zero_dw, uint32_t leader) {
   const uint32_t sb = smem_base + OFF_SLOT + (uint32_t)slot * SLOT;
-  {  // wgrad: dW_l[128, 80] += ZC[128, 4P] * AC[80, 4P]^T
+  {  // wgrad: dW_l[128, 80] += Zbar[128, 4P] * Act[80, 4P]^T, contraction over n = 4p + s.  Both operands are the row-per-neuron
+     // images the epilogue already wrote for the MN-major reads, now read K-MAJOR with the same descriptor layout type 1
+     // (measured, scripts/probe_mma.cu: rows 128 B apart in groups of 4, SBO between groups, a K step is one 32-byte chunk).
     const int l = 2 * L - s;
     const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
     const uint32_t dw_col = tmem + (uint32_t)((l - 1) * NW);
-    const uint32_t zh = sb + 2 * RB;
-    constexpr uint32_t CHI = desc_hi(128);
-    const uint32_t ah0 = desc_lo(zh, C_SP), al0 = desc_lo(zh + CB, C_SP);
-    const uint32_t bh0 = desc_lo(zh + 2 * CB, C_SP), bl0 = desc_lo(zh + 3 * CB, C_SP);
+    constexpr uint32_t RHI = desc_hi_t(R_ATOM, 1);
+    const uint32_t ah0 = desc_lo(sb, 0), al0 = desc_lo(sb + RB, 0);
+    const uint32_t bh0 = desc_lo(sb + 2 * RB, 0), bl0 = desc_lo(sb + 3 * RB, 0);
 #pragma unroll
     for (int ks = 0; ks < NCOL / 8; ++ks) {
-      const uint32_t d = ks * ((2 * C_SP) >> 4);
-      mma_tf32_elect2(dw_col, al0 + d, CHI, bh0 + d, CHI, idesc, !(zero_dw && ks == 0), leader);
-      mma_tf32_elect2(dw_col, ah0 + d, CHI, bl0 + d, CHI, idesc, 1, leader);
-      mma_tf32_elect2(dw_col, ah0 + d, CHI, bh0 + d, CHI, idesc, 1, leader);
+      const uint32_t d = ks * (32 >> 4);
+      mma_tf32_elect2(dw_col, al0 + d, RHI, bh0 + d, RHI, idesc, !(zero_dw && ks == 0), leader);
+      mma_tf32_elect2(dw_col, ah0 + d, RHI, bl0 + d, RHI, idesc, 1, leader);
+      mma_tf32_elect2(dw_col, ah0 + d, RHI, bh0 + d, RHI, idesc, 1, leader);
     }
   }
 }
@@ -171,7 +170,6 @@ struct Epi {
   bool active;           // j < KP
   uint32_t lane_addr;    // TMEM lane field of this warp's quadrant
   uint32_t r_off;        // byte offset of this thread's float4 (point pi = 0; pi = 1: + 16) in an R image
-  uint32_t c_off;        // byte offset of this thread's float4 (point pi = 0; pi = 1: + C_SP) in a C image
 };
 
 __device__ __forceinline__ void split4(const float v[4], float hi[4], float lo[4]) {
@@ -183,12 +181,6 @@ __device__ __forceinline__ void store_R(uint32_t rimg, const Epi& e, int pi, con
   sts4(rimg + e.r_off + pi * 16, hi[0], hi[1], hi[2], hi[3]);
   sts4(rimg + RB + e.r_off + pi * 16, lo[0], lo[1], lo[2], lo[3]);
 }
-// ... -> C image pair at `cimg` (hi; lo follows CB bytes later)
-__device__ __forceinline__ void store_C(uint32_t cimg, const Epi& e, int pi, const float hi[4], const float lo[4]) {
-  sts4(cimg + e.c_off + pi * C_SP, hi[0], hi[1], hi[2], hi[3]);
-  sts4(cimg + CB + e.c_off + pi * C_SP, lo[0], lo[1], lo[2], lo[3]);
-}
-
 // tanh jet of one point: z -> activations
 __device__ __forceinline__ void jet_fwd(const float z[4], float v[4]) {
   const float t = nsf_tanh_fast(z[0]);
@@ -342,7 +334,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     e.active = e.j < KP;
     e.lane_addr = (uint32_t)(e.q * 32) << 16;
     e.r_off = (uint32_t)(e.j >> 2) * R_ATOM + (uint32_t)(e.j & 3) * 128 + (uint32_t)((e.sub ^ (e.j & 3)) * 32);
-    e.c_off = (uint32_t)(2 * e.sub) * C_SP + (uint32_t)(e.j >> 3) * 128 + (uint32_t)(e.j & 7) * 16;
     const int jj = e.active ? e.j : 0;
     const float* pk = a.pk;
     const float w0x = __ldg(pk + g.pk_w0x() + jj), w0y = __ldg(pk + g.pk_w0y() + jj), b0 = __ldg(pk + g.pk_b0() + jj);
@@ -410,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             float av[4], hi[4], lo[4];
             act_from_stash(st_lm1[pi], av);
             split4(av, hi, lo);
-            store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
+            store_R(sb + 2 * RB, e, pi, hi, lo);
           }
         }
       }
@@ -537,7 +528,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
               if (L >= 2) {
                 split4(zb, hi, lo);
                 store_R(sb, e, pi, hi, lo);
-                store_C(sb + 2 * RB, e, pi, hi, lo);
               }
             }
             gb[L - 1] += sb0;
@@ -558,13 +548,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             sb0 += zb[0];
             if (l >= 1) {
               split4(zb, hi, lo);
+              // the weight-gradient MMAs of this stage still read both image pairs of the slot: wait for them
+              if (pi == 0) { mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u); }
               store_R(sb, e, pi, hi, lo);
-              if (pi == 0) { mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u); }   // C images: their last readers are done
-              store_C(sb + 2 * RB, e, pi, hi, lo);
               float av[4];
               act_from_stash(st_lm1[pi], av);
               split4(av, hi, lo);
-              store_C(sb + 2 * RB + 2 * CB, e, pi, hi, lo);
+              store_R(sb + 2 * RB, e, pi, hi, lo);
             } else {
               gw0x += fmaf(zb[0], xv[pi], zb[1]); gw0y += fmaf(zb[0], yv[pi], zb[2]);
             }

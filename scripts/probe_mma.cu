@@ -190,8 +190,16 @@ static void run_decode(const char* name, DecodeCfg c, float* d_out, std::vector<
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
   CK(cudaSetDevice(0));
+  if (argc == 9) {   // single decode: which mn ltype lbo sbo N M start   (one process per configuration: a bad descriptor faults)
+    CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024));
+    float* d_out1; CK(cudaMalloc(&d_out1, 2 * 128 * 256 * sizeof(float)));
+    std::vector<float> h1(2 * 128 * 256);
+    DecodeCfg c{atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), (uint32_t)atoi(argv[4]), (uint32_t)atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), (uint32_t)atoi(argv[8])};
+    run_decode("cli", c, d_out1, h1);
+    return 0;
+  }
   CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024));
   CK(cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   float* d_out; CK(cudaMalloc(&d_out, 2 * 128 * 256 * sizeof(float)));
