@@ -352,8 +352,8 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
 #ifndef NSF_EMU
   if (n_f > 0 && effective_path(ctx) == 2) {   // one persistent CTA per SM, a pair of 8-point tiles per iteration
     NSF_TRY(nsf_umma_init(ctx));
-    const long long pairs = (n_f + 15) / 16;
-    grids[0] = (int)(pairs < ctx->sms ? pairs : ctx->sms);
+    const long long groups = (n_f + nsf_umma_group_points() - 1) / nsf_umma_group_points();
+    grids[0] = (int)(groups < ctx->sms ? groups : ctx->sms);
   }
   if (n_f > 0 && effective_path(ctx) == 3) {
     NSF_TRY(nsf_umma2_init(ctx));

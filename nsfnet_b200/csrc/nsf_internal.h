@@ -92,6 +92,7 @@ int nsf_value_fwd_launch(const NsfNetGeom& g, int sms, const float* flat, const 
 
 // nsf_umma_jet.cu (CUDA build only) ---------------------------------------------------------------
 int nsf_umma_supported(const NsfNetGeom& g);
+int nsf_umma_group_points();
 int nsf_umma_init(NsfCtx* ctx);
 void nsf_umma_free(NsfCtx* ctx);
 int nsf_umma_stage_cycles(NsfCtx* ctx, double* out);

@@ -42,16 +42,17 @@ namespace {
 
 constexpr int KP = 80;            // hidden width handled by this kernel
 constexpr int P = 8;              // points per tile slot
+constexpr int NS = 3;             // tile slots in flight (three hide the MMA -> epilogue -> MMA latency of a slot behind the other two)
 constexpr int NCOL = 4 * P;       // MMA N of the forward / dgrad contractions
 constexpr int NW = 80;            // MMA N of the weight-gradient contraction (columns of dW_l)
-constexpr int MAXL = 6;           // (L-1)*80 + 2*32 <= 512 TMEM columns
+constexpr int MAXL = 6;           // (L-1)*80 + NS*32 <= 512 TMEM columns
 constexpr int PPT = 2;            // points per epilogue thread and stage
 constexpr int NSUB = P / PPT;     // epilogue warps per TMEM lane quadrant
 constexpr int NWARPS = 4 * NSUB - 1;   // warps 4*sub + q, q = 0..2 epilogue; warp 3 issuer; warps 7, 11 idle
 constexpr int NTHREADS = NWARPS * 32;  // 480
 constexpr int NEPI = 3 * NSUB * 32;    // 384 epilogue threads
 constexpr int ISSUER_WARP = 3;
-constexpr int FLUSH = 32;         // tile pairs between flushes of the TMEM weight-gradient accumulators
+constexpr int FLUSH = 21;         // tile groups (NS x P points) between flushes of the TMEM weight-gradient accumulators
 
 constexpr uint32_t W_SBO = (KP / 4) * 128;      // 2560: 8-row band of a weight image
 constexpr uint32_t IMG = (KP / 8) * W_SBO;      // 25600: one weight image (hi or lo)
@@ -60,8 +61,8 @@ constexpr uint32_t R_ATOM = 512;                // 4 neurons x 128 B (32 columns
 constexpr uint32_t RB = (KP / 4) * R_ATOM;      // 10240: one R image
 constexpr uint32_t SLOT = 4 * RB;                // 40960: R hi, R lo (z-bar or activations), RA hi, RA lo (activations of the layer below)
 constexpr uint32_t OFF_SLOT = 2 * WBUF;         // 102400
-constexpr uint32_t OFF_MISC = OFF_SLOT + 2 * SLOT;   // 225280
-constexpr uint32_t MISC = 1536;
+constexpr uint32_t OFF_MISC = OFF_SLOT + NS * SLOT;  // 225280
+constexpr uint32_t MISC = 2560;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;     // 226816 <= 232448
 static_assert(OFF_SLOT % 1024 == 0 && SLOT % 1024 == 0, "R images must keep the 512-byte swizzle phase");
 
@@ -74,24 +75,24 @@ struct UArgs {
   float inv_Re, vis_t0, alpha_evm, cs1, cs2, k4, c_eq;
   int has_evm;
   float* resid_out; float* vis_t_out; float* ebar_out;
-  float* stash;          // [grid][2][L][P][KP][4]
+  float* stash;          // [grid][NS][L][P][KP][4]
   float* scratch;        // gradient rows [grid][gs_row]
   int n_pairs;
   long long* dbg;        // optional [grid][16 warps][16] cycle counters (nsf_get_stage_cycles)
 };
 
 struct Misc {
-  uint64_t mbar[2];      // "done": the slot's MMAs have completed (tcgen05.commit)
+  uint64_t mbar[NS];     // "done": the slot's MMAs have completed (tcgen05.commit)
   uint64_t wbar[2];      // (diagnostics only)
-  uint64_t ready[2];     // the slot's operands are written and its previous results consumed (one arrival per epilogue warp);
+  uint64_t ready[NS];    // the slot's operands are written and its previous results consumed (one arrival per epilogue warp);
                          // ready[0] also carries the stage's weight image (producer arrival + TMA complete_tx): every
                          // mbarrier poll costs 200+ cycles while the MMAs saturate shared memory, so the issuer polls once
   uint64_t wfree[2];     // every MMA reading weight buffer b has completed (tcgen05.commit)
-  uint64_t wdone[2];     // the slot's weight-gradient MMAs (readers of its C images) have completed (tcgen05.commit)
+  uint64_t wdone[NS];    // the slot's weight-gradient MMAs (readers of its C images) have completed (tcgen05.commit)
   uint32_t tmem_base;
   uint32_t pad[3];
-  float ov[2][P][16];    // outputs / output adjoints [slot][p][4*s + o]
-  float red[P][12];      // per-point-lane loss sums and output-bias gradient partials
+  alignas(16) float ov[NS][P][16];   // outputs / output adjoints [slot][p][4*s + o]
+  alignas(16) float red[P][12];      // per-point-lane loss sums and output-bias gradient partials
 };
 static_assert(sizeof(Misc) <= MISC, "misc region too small");
 
@@ -241,15 +242,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
   if (warp == 0) tmem_alloc(&misc->tmem_base, 512);
   if (tid == 0) {
     if (smem_base & 1023u) __trap();                // the swizzled R images assume a 1 KB aligned window
-    mbar_init(&misc->mbar[0], 1); mbar_init(&misc->mbar[1], 1);
-    mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
-    mbar_init(&misc->ready[0], NEPI / 32 + 1); mbar_init(&misc->ready[1], NEPI / 32);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&misc->mbar[i], 1); mbar_init(&misc->wdone[i], 1);
+      mbar_init(&misc->ready[i], NEPI / 32 + (i == 0 ? 1 : 0));
+    }
     mbar_init(&misc->wfree[0], 1); mbar_init(&misc->wfree[1], 1);
-    mbar_init(&misc->wdone[0], 1); mbar_init(&misc->wdone[1], 1);
     mbar_fence_init();
   }
   // zero the operand slots once (the M = 128 operand fetch reads 48 rows past the 80 real ones) and the loss sums
-  for (uint32_t i = tid * 16; i < 2 * SLOT; i += NTHREADS * 16) *reinterpret_cast<float4*>(smem + OFF_SLOT + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t i = tid * 16; i < NS * SLOT; i += NTHREADS * 16) *reinterpret_cast<float4*>(smem + OFF_SLOT + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid < P * 12) (&misc->red[0][0])[tid] = 0.f;
   fence_async_smem();
   tc_fence_before();
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       for (int s = 1; s < NSTAGE; ++s) {
         const uint32_t b = stage_ctr & 1u;
 #pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < NS; ++slot) {
           long long t0 = 0, t1 = 0;
           if (DBG) t0 = clock64();
           mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u); rphases ^= 1u << slot;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           // completion barrier (they read the C images, which that epilogue rewrites last)
           issue_main<L>(smem_base, tmem, s, slot, (int)b, leader);
           mma_commit_elect(&misc->mbar[slot], leader);
-          if (slot == 1) mma_commit_elect(&misc->wfree[b], leader);
+          if (slot == NS - 1) mma_commit_elect(&misc->wfree[b], leader);
           if (s > L) {
             issue_wgrad<L>(smem_base, tmem, s, slot, (pr % FLUSH) == 0 && slot == 0, leader);
             mma_commit_elect(&misc->wdone[slot], leader);
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     for (int l = 1; l < MAXL; ++l) bias[l] = (l < L) ? __ldg(pk + g.pk_b(l) + jj) : 0.f;
     const float bo = (e.q == 0 && lane < 3) ? __ldg(pk + g.pk_bl() + lane) : 0.f;
     // this thread's float4 of (slot 0, layer 0, point 2*sub); + slot*L*P*KP + l*P*KP + pi*KP float4s
-    float4* stash_thr = TRAIN ? reinterpret_cast<float4*>(a.stash) + (size_t)blockIdx.x * (2 * L * P * KP) + (size_t)(2 * e.sub) * KP + jj : nullptr;
+    float4* stash_thr = TRAIN ? reinterpret_cast<float4*>(a.stash) + (size_t)blockIdx.x * (NS * L * P * KP) + (size_t)(2 * e.sub) * KP + jj : nullptr;
     float* grow = TRAIN ? a.scratch + (size_t)blockIdx.x * g.gs_row() : nullptr;
     // per-thread gradient partials (this neuron, this thread's share of the points)
     float gw0x = 0.f, gw0y = 0.f, gwl[3] = {0.f, 0.f, 0.f};
@@ -580,19 +581,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; tcnt[cls + 4] += 1; }
     };
 
-    const long long pair_stride = (long long)gridDim.x * 2 * P;
-    long long pA = (long long)blockIdx.x * 2 * P;                         // first point of slot A's tile; slot B follows
-    if (my_pairs > 0) { stage_step(0, 0, pA); stage_step(0, 1, pA); }
+    const long long pair_stride = (long long)gridDim.x * NS * P;
+    long long pA = (long long)blockIdx.x * NS * P;                        // first point of slot 0's tile; the other slots follow
+    if (my_pairs > 0) {
+#pragma unroll 1
+      for (int slot = 0; slot < NS; ++slot) stage_step(0, slot, pA);
+    }
     for (int pr = 0; pr < my_pairs; ++pr, pA += pair_stride) {
 #pragma unroll
       for (int s = 1; s < NSTAGE - 1; ++s) {
 #pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) stage_step(s, slot, pA);
+        for (int slot = 0; slot < NS; ++slot) stage_step(s, slot, pA);
       }
       // last stage of this pair fused with stage 0 of the next pair, slot by slot: the issuer gets slot A's first
       // operands of the next tile while slot B still finishes, so the tensor pipe does not drain between pairs
 #pragma unroll 1
-      for (int slot = 0; slot < 2; ++slot) {
+      for (int slot = 0; slot < NS; ++slot) {
         stage_step(NSTAGE - 1, slot, pA);
         if (pr + 1 < my_pairs) stage_step(0, slot, pA + pair_stride);
       }
@@ -695,6 +699,9 @@ struct UmmaState {
 
 #define NSF_TRY_INIT(ctx) do { int rc__ = nsf_umma_init(ctx); if (rc__ != NSF_OK) return rc__; } while (0)
 
+// collocation points one CTA takes per iteration (NS tiles of P points)
+int nsf_umma_group_points() { return NS * P; }
+
 int nsf_umma_supported(const NsfNetGeom& g) { return g.H == KP && g.n_out == 3 && g.L >= 2 && g.L <= MAXL; }
 
 typedef void (*JetKernel)(const UArgs);
@@ -721,11 +728,11 @@ int nsf_umma_init(NsfCtx* ctx) {
   s->grid = ctx->sms;
   if (s->grid > ctx->main.rows) s->grid = ctx->main.rows;
   NSF_CUDA_OK(cudaMalloc((void**)&s->wimg, (size_t)(2 * g.L - 1) * WBUF));
-  NSF_CUDA_OK(cudaMalloc((void**)&s->stash, (size_t)s->grid * 2 * g.L * P * KP * 4 * sizeof(float)));
+  NSF_CUDA_OK(cudaMalloc((void**)&s->stash, (size_t)s->grid * NS * g.L * P * KP * 4 * sizeof(float)));
   for (int train = 0; train < 2; ++train)
     for (int dbg = 0; dbg <= train; ++dbg)
       NSF_CUDA_OK(cudaFuncSetAttribute(jet_kernel(g.L, train != 0, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  ctx->ws_bytes += (long long)(2 * g.L - 1) * WBUF + (long long)s->grid * 2 * g.L * P * KP * 16;
+  ctx->ws_bytes += (long long)(2 * g.L - 1) * WBUF + (long long)s->grid * NS * g.L * P * KP * 16;
   ctx->umma = s;
   return NSF_OK;
 }
@@ -756,7 +763,7 @@ int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_param
   a.resid_out = k.resid_out; a.vis_t_out = k.vis_t_out; a.ebar_out = k.ebar_out;
   a.stash = train ? s->stash : nullptr;
   a.scratch = train ? k.scratch : nullptr;
-  a.n_pairs = (int)((k.n + 2 * P - 1) / (2 * P));
+  a.n_pairs = (int)((k.n + NS * P - 1) / (NS * P));
   a.dbg = s->dbg_on ? s->dbg : nullptr;
   int grid = a.n_pairs < s->grid ? a.n_pairs : s->grid;
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }

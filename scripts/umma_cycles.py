@@ -24,5 +24,5 @@ for w in range(15):
     elif (w & 3) != 3:
         print(f"warp {w:2d} q{w & 3} sub{w >> 2}: fwd " + "  ".join(f"{nm}={v / max(r[4], 1):7.1f}" for nm, v in zip(names[:4], r[:4])) +
               "  | rev " + "  ".join(f"{nm}={v / max(r[9], 1):7.1f}" for nm, v in zip(names[:4], r[5:9])) + f"  steps={r[4]:.0f}+{r[9]:.0f}")
-pairs = c[3][4] / 22.0
-print("issuer operand wait per pair by stage s (both slots):", "  ".join(f"s{i}={c[7][i] / max(pairs, 1):.0f}" for i in range(1, 12)))
+pairs = c[3][4] / 33.0   # stage-slots per tile group: 11 MMA stages x 3 slots
+print("issuer operand wait per tile group by stage s (all slots):", "  ".join(f"s{i}={c[7][i] / max(pairs, 1):.0f}" for i in range(1, 12)))
