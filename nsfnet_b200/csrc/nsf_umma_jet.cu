@@ -62,7 +62,7 @@ constexpr uint32_t RB = (KP / 4) * R_ATOM;      // 10240: one R image
 constexpr uint32_t SLOT = 4 * RB;                // 40960: R hi, R lo (z-bar or activations), RA hi, RA lo (activations of the layer below)
 constexpr uint32_t OFF_SLOT = 2 * WBUF;         // 102400
 constexpr uint32_t OFF_MISC = OFF_SLOT + NS * SLOT;  // 225280
-constexpr uint32_t MISC = 2560;
+constexpr uint32_t MISC = 3072;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;     // 226816 <= 232448
 static_assert(OFF_SLOT % 1024 == 0 && SLOT % 1024 == 0, "R images must keep the 512-byte swizzle phase");
 
@@ -92,7 +92,7 @@ struct Misc {
   uint32_t tmem_base;
   uint32_t pad[3];
   alignas(16) float ov[NS][P][16];   // outputs / output adjoints [slot][p][4*s + o]
-  alignas(16) float red[P][12];      // per-point-lane loss sums and output-bias gradient partials
+  alignas(16) float red[NS * P][12]; // per-point-lane loss sums and output-bias gradient partials
 };
 static_assert(sizeof(Misc) <= MISC, "misc region too small");
 
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
   }
   // zero the operand slots once (the M = 128 operand fetch reads 48 rows past the 80 real ones) and the loss sums
   for (uint32_t i = tid * 16; i < NS * SLOT; i += NTHREADS * 16) *reinterpret_cast<float4*>(smem + OFF_SLOT + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid < P * 12) (&misc->red[0][0])[tid] = 0.f;
+  if (tid < NS * P * 12) (&misc->red[0][0])[tid] = 0.f;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -358,8 +358,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 #pragma unroll
     for (int i = 0; i < 10; ++i) tcnt[i] = 0;
 
+    // residuals, loss sums and adjoint seeds of point p of a slot's tile from its gathered outputs (one thread per point)
+    auto residual_point = [&](const int slot, const int p, const long long p0, const int nvalid, const float pre_e, const float pre_vtm,
+                              const float pre_w) {
+      const bool ok = p < nvalid;
+      const long long gp = p0 + p;
+      float* ov = misc->ov[slot][p];
+      float* red = misc->red[slot * P + p];
+      const float u = ov[0], v = ov[1];
+      const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
+      const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
+      const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
+      float ee = 0.f, vis = 0.f;
+      if (a.has_evm) {
+        ee = pre_e;
+        vis = ok ? fminf(a.vis_t0, pre_vtm) : a.vis_t0;
+      }
+      const float nu = a.inv_Re + vis;
+      const float eq1 = (u * ux + v * uy) + px - nu * ul;
+      const float eq2 = (u * vx + v * vy) + py - nu * vl;
+      const float eq3 = ux + vy;
+      const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
+      const float w = pre_w;
+      if (ok) {
+        red[0] += w * eq1 * eq1; red[1] += w * eq2 * eq2; red[2] += w * eq3 * eq3; red[3] += w * eq4 * eq4;
+        red[4] += vis; red[5] += 1.f;
+        if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
+        if (a.vis_t_out) a.vis_t_out[gp] = vis;
+        if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
+      }
+      if (TRAIN) {
+        const float cw = ok ? a.c_eq * w : 0.f;
+        const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
+        const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
+        const float g3 = 2.f * cw * eq3;
+        const float g4 = a.k4 * cw * eq4;
+        ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
+        ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
+        ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
+        ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
+        red[6] += ov[0]; red[7] += ov[1]; red[8] += ov[2];
+        if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
+      }
+    };
+
     // one (stage, slot) step of this warp's share of a tile; `s` is a literal / unrolled constant at every call site
-    auto stage_step = [&](const int s, const int slot, const long long pA) {
+    // `part` splits the output stage (s = L): 1 = up to publishing the raw outputs, 2 = from the adjoint seeds on, 0 = all of it
+    auto stage_step = [&](const int s, const int slot, const long long pA, const int part = 0) {
       const long long rem = a.n - pA - (long long)slot * P;
       const int nvalid = (int)(rem < 0 ? 0 : (rem < P ? rem : P));
       const long long p0 = pA + slot * P;
@@ -373,8 +418,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       if (is_rev && e.active) {
 #pragma unroll
         for (int pi = 0; pi < PPT; ++pi) {
-          st_l[pi] = __ldcs(st_slot + lrev * (P * KP) + pi * KP);
-          if (lrev >= 1) st_lm1[pi] = __ldcs(st_slot + (lrev - 1) * (P * KP) + pi * KP);
+          if (part != 1) st_l[pi] = __ldcs(st_slot + lrev * (P * KP) + pi * KP);
+          if (lrev >= 1 && part != 2) st_lm1[pi] = __ldcs(st_slot + (lrev - 1) * (P * KP) + pi * KP);
         }
       }
       float4 stv[PPT];                                                  // (t, zx, zy, z_lap) of a forward stage, stashed after the hand-over
@@ -390,8 +435,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       // output stage: the residual threads' per-point inputs come from L2 as well; and the C image of a^{L-2} depends
       // on the stash only (its last readers finished with the previous tile), so it is written before the wait
       float pre_e = 0.f, pre_vtm = 0.f, pre_w = 1.f;
-      if (s == L) {
-        if (tid < P && tid < nvalid) {
+      if (s == L && part != 2) {
+        if (part == 0 && tid < P && tid < nvalid) {
           const long long gp = p0 + tid;
           if (a.has_evm) { pre_e = __ldg(a.e_in + gp); pre_vtm = a.vtm_in ? __ldg(a.vtm_in + gp) : a.vis_t0; }
           if (a.w) pre_w = __ldg(a.w + gp);
@@ -409,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
       long long t0 = 0, t1 = 0;
       if (DBG) t0 = clock64();
-      if (s >= 1) {
+      if (s >= 1 && !(s == L && part == 2)) {
         mbar_wait(&misc->mbar[slot], (mphases >> slot) & 1u);
         mphases ^= 1u << slot;
         tc_fence_after();
@@ -447,6 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         }
       } else if (s == L) {
         // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
+        if (part != 2) {
         float o[PPT][4];
         tmem_ld8(d_addr, &o[0][0]);
         tmem_ld_wait();
@@ -460,51 +506,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             misc->ov[slot][p][3 * 4 + lane] = o[pi][3];
           }
         }
-        epi_bar();
-        if (tid < P) {
-          const int p = tid;
-          const bool ok = p < nvalid;
-          const long long gp = p0 + p;
-          float* ov = misc->ov[slot][p];
-          float* red = misc->red[p];
-          const float u = ov[0], v = ov[1];
-          const float ux = a.cs1 * ov[4], vx = a.cs1 * ov[5], px = a.cs1 * ov[6];
-          const float uy = a.cs1 * ov[8], vy = a.cs1 * ov[9], py = a.cs1 * ov[10];
-          const float ul = a.cs2 * ov[12], vl = a.cs2 * ov[13];
-          float ee = 0.f, vis = 0.f;
-          if (a.has_evm) {
-            ee = pre_e;
-            vis = ok ? fminf(a.vis_t0, pre_vtm) : a.vis_t0;
-          }
-          const float nu = a.inv_Re + vis;
-          const float eq1 = (u * ux + v * uy) + px - nu * ul;
-          const float eq2 = (u * vx + v * vy) + py - nu * vl;
-          const float eq3 = ux + vy;
-          const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
-          const float w = pre_w;
-          if (ok) {
-            red[0] += w * eq1 * eq1; red[1] += w * eq2 * eq2; red[2] += w * eq3 * eq3; red[3] += w * eq4 * eq4;
-            red[4] += vis; red[5] += 1.f;
-            if (a.resid_out) { a.resid_out[gp] = eq1; a.resid_out[a.n + gp] = eq2; a.resid_out[2 * a.n + gp] = eq3; a.resid_out[3 * a.n + gp] = eq4; }
-            if (a.vis_t_out) a.vis_t_out[gp] = vis;
-            if (a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
-          }
-          if (TRAIN) {
-            const float cw = ok ? a.c_eq * w : 0.f;
-            const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
-            const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
-            const float g3 = 2.f * cw * eq3;
-            const float g4 = a.k4 * cw * eq4;
-            ov[0] = g1 * ux + g2 * vx + g4 * eq1; ov[1] = g1 * uy + g2 * vy + g4 * eq2; ov[2] = 0.f;
-            ov[4] = a.cs1 * (g1 * u + g3); ov[5] = a.cs1 * (g2 * u); ov[6] = a.cs1 * g1;
-            ov[8] = a.cs1 * (g1 * v); ov[9] = a.cs1 * (g2 * v + g3); ov[10] = a.cs1 * g2;
-            ov[12] = -a.cs2 * nu * g1; ov[13] = -a.cs2 * nu * g2; ov[14] = 0.f;
-            red[6] += ov[0]; red[7] += ov[1]; red[8] += ov[2];
-            if (a.ebar_out && ok) a.ebar_out[gp] = -g4;
-          }
         }
-        if (TRAIN) {
+        if (part == 0) {
           epi_bar();
+          if (tid < P) residual_point(slot, tid, p0, nvalid, pre_e, pre_vtm, pre_w);
+          if (TRAIN) epi_bar();
+        }
+        if (TRAIN && part != 1) {
           if (e.active) {
             float sb0 = 0.f;
 #pragma unroll
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         wdphases ^= 1u << slot;
       }
       if (DBG) { t0 = clock64(); tcnt[cls + 1] += t0 - t1; }
-      if (s < NSTAGE - 1) {
+      if (s < NSTAGE - 1 && !(s == L && part == 1)) {
         // hand the slot to the issuer: operands visible to the async proxy, TMEM reads retired
         fence_async_smem();
         tc_fence_before();
@@ -590,8 +598,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     for (int pr = 0; pr < my_pairs; ++pr, pA += pair_stride) {
 #pragma unroll
       for (int s = 1; s < NSTAGE - 1; ++s) {
+        if (s == L) {
+          // output stage of all slots at once: one residual thread per point of the group (NS x P), two CTA barriers per
+          // group instead of two per slot; its epilogue is what the tensor pipe waits for in this part of the tile
+          const int rs = tid / P, rp = tid % P;
+          const long long rp0 = pA + (long long)rs * P;
+          const long long rrem = a.n - rp0;
+          const int rnv = (int)(rrem < 0 ? 0 : (rrem < P ? rrem : P));
+          float pre_e = 0.f, pre_vtm = 0.f, pre_w = 1.f;
+          if (tid < NS * P && rp < rnv) {
+            if (a.has_evm) { pre_e = __ldg(a.e_in + rp0 + rp); pre_vtm = a.vtm_in ? __ldg(a.vtm_in + rp0 + rp) : a.vis_t0; }
+            if (a.w) pre_w = __ldg(a.w + rp0 + rp);
+          }
 #pragma unroll 1
-        for (int slot = 0; slot < NS; ++slot) stage_step(s, slot, pA);
+          for (int slot = 0; slot < NS; ++slot) stage_step(s, slot, pA, 1);
+          epi_bar();
+          if (tid < NS * P) residual_point(rs, rp, rp0, rnv, pre_e, pre_vtm, pre_w);
+          epi_bar();
+#pragma unroll 1
+          for (int slot = 0; slot < NS; ++slot) stage_step(s, slot, pA, 2);
+        } else {
+#pragma unroll 1
+          for (int slot = 0; slot < NS; ++slot) stage_step(s, slot, pA);
+        }
       }
       // last stage of this pair fused with stage 0 of the next pair, slot by slot: the issuer gets slot A's first
       // operands of the next tile while slot B still finishes, so the tensor pipe does not drain between pairs
@@ -646,12 +675,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       }
       if (tid < NSF_LOSS_SLOTS) {
         float v = 0.f;
-        if (tid < 6) for (int p = 0; p < P; ++p) v += misc->red[p][tid];
+        if (tid < 6) for (int p = 0; p < NS * P; ++p) v += misc->red[p][tid];
         growx[g.gs_loss() + tid] = v;
       }
       if (TRAIN && tid < 4) {
         float v = 0.f;
-        if (tid < 3) for (int p = 0; p < P; ++p) v += misc->red[p][6 + tid];
+        if (tid < 3) for (int p = 0; p < NS * P; ++p) v += misc->red[p][6 + tid];
         growx[g.gs_bl() + tid] = v;
       }
     }
