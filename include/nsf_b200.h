@@ -103,7 +103,7 @@ int nsf_create(int device, const NsfNetDesc* main_net, const NsfNetDesc* evm_or_
 int nsf_destroy(NsfCtx* ctx);
 
 /* Select the kernel family of the hidden-layer contractions: 0 = auto (tcgen05 when the shape is
- * covered, else FFMA), 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 tile-major kernel, 3 = tcgen05
+ * covered, else FFMA), 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 tile-major kernel (default for hidden = 80), 3 = tcgen05
  * 3xTF32 layer-major kernel (weights in tensor memory); 2 / 3 return NSF_E_SHAPE if the shape is not covered. */
 int nsf_set_path(NsfCtx* ctx, int path);
 /* Tuning knob of the layer-major kernel: 12-point tiles per super-batch (1..8, 0 = default 4). */
@@ -141,6 +141,9 @@ int nsf_get_stage_cycles(NsfCtx* ctx, double* out);
  *   loss_parts             : device float[NSF_LOSS_SLOTS], overwritten
  *   residuals_out          : NULL or device float[4*n_f] = eq1|eq2|eq3|eq4 (eq4 = 0 without EVM)
  *   e_out, vis_t_out       : NULL or device float[n_f] (self.evm, self.vis_t)
+ *   Asynchronous on `stream`.  With the tcgen05 kernel the data blocks are forked onto a library-owned non-blocking
+ *   side stream (event fork / join, so it is CUDA-graph capturable) and joined on `stream` before the call's last
+ *   kernels; everything the call writes is ordered on `stream` when it returns.
  */
 int nsf_step(NsfCtx* ctx, const float* params_main, const float* params_evm,
              const float* x, const float* y, const float* w,

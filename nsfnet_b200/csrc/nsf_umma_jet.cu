@@ -171,17 +171,30 @@ struct Epi {
   bool active;           // j < KP
   uint32_t lane_addr;    // TMEM lane field of this warp's quadrant
   uint32_t r_off;        // byte offset of this thread's float4 (point pi = 0; pi = 1: + 16) in an R image
+  uint32_t r_offA, r_offB; // first / second float4 store of a point pair (see store_R_pair)
+  bool sw;               // this thread stores its point 1 first
 };
 
 __device__ __forceinline__ void split4(const float v[4], float hi[4], float lo[4]) {
 #pragma unroll
   for (int s = 0; s < 4; ++s) split_tf32_fast(v[s], hi[s], lo[s]);
 }
-// the 4 streams of point pi -> R image pair at `rimg` (hi; lo follows RB bytes later)
-__device__ __forceinline__ void store_R(uint32_t rimg, const Epi& e, int pi, const float hi[4], const float lo[4]) {
-  sts4(rimg + e.r_off + pi * 16, hi[0], hi[1], hi[2], hi[3]);
-  sts4(rimg + RB + e.r_off + pi * 16, lo[0], lo[1], lo[2], lo[3]);
+// the 4 streams of this thread's two points -> R image pair at `rimg` (hi; lo follows RB bytes later).  A point's float4
+// lands in the 16-byte half (p & 1) of a 32-byte chunk whose position depends on (neuron & 3) only, so a plain
+// "all lanes store point 0, then point 1" has lanes j and j+4 on the same banks (2-way conflict on every store).
+// Lanes with (j >> 2) & 1 therefore store their point 1 first: the 8 lanes of a quarter-warp hit 8 different bank groups.
+__device__ __forceinline__ void store_R_pair(uint32_t rimg, const Epi& e, const float v0[4], const float v1[4]) {
+  float a[4], b[4], hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a[i] = e.sw ? v1[i] : v0[i]; b[i] = e.sw ? v0[i] : v1[i]; }
+  split4(a, hi, lo);
+  sts4(rimg + e.r_offA, hi[0], hi[1], hi[2], hi[3]);
+  sts4(rimg + RB + e.r_offA, lo[0], lo[1], lo[2], lo[3]);
+  split4(b, hi, lo);
+  sts4(rimg + e.r_offB, hi[0], hi[1], hi[2], hi[3]);
+  sts4(rimg + RB + e.r_offB, lo[0], lo[1], lo[2], lo[3]);
 }
+
 // tanh jet of one point: z -> activations
 __device__ __forceinline__ void jet_fwd(const float z[4], float v[4]) {
   const float t = nsf_tanh_fast(z[0]);
@@ -335,6 +348,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     e.active = e.j < KP;
     e.lane_addr = (uint32_t)(e.q * 32) << 16;
     e.r_off = (uint32_t)(e.j >> 2) * R_ATOM + (uint32_t)(e.j & 3) * 128 + (uint32_t)((e.sub ^ (e.j & 3)) * 32);
+    e.sw = ((e.j >> 2) & 1) != 0;
+    e.r_offA = e.r_off + (e.sw ? 16u : 0u); e.r_offB = e.r_off + (e.sw ? 0u : 16u);
     const int jj = e.active ? e.j : 0;
     const float* pk = a.pk;
     const float w0x = __ldg(pk + g.pk_w0x() + jj), w0y = __ldg(pk + g.pk_w0y() + jj), b0 = __ldg(pk + g.pk_b0() + jj);
@@ -443,12 +458,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         }
         if (TRAIN && L >= 2 && e.active) {
 #pragma unroll
-          for (int pi = 0; pi < PPT; ++pi) {
-            float av[4], hi[4], lo[4];
-            act_from_stash(st_lm1[pi], av);
-            split4(av, hi, lo);
-            store_R(sb + 2 * RB, e, pi, hi, lo);
-          }
+          float av[PPT][4];
+#pragma unroll
+          for (int pi = 0; pi < PPT; ++pi) act_from_stash(st_lm1[pi], av[pi]);
+          store_R_pair(sb + 2 * RB, e, av[0], av[1]);
         }
       }
       const int cls = (s > L) ? 5 : 0;      // counter block: forward (incl. output stage) / reverse
@@ -465,14 +478,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         // ---- layer 0 (K = 2) -------------------------------------------------------------
         if (e.active) {
 #pragma unroll
+          float v[PPT][4];
+#pragma unroll
           for (int pi = 0; pi < PPT; ++pi) {
             const float z[4] = {fmaf(w0x, xv[pi], fmaf(w0y, yv[pi], b0)), w0x, w0y, 0.f};
-            float v[4], hi[4], lo[4];
-            jet_fwd(z, v);
-            stv[pi] = make_float4(v[0], z[1], z[2], z[3]);
-            split4(v, hi, lo);
-            store_R(sb, e, pi, hi, lo);
+            jet_fwd(z, v[pi]);
+            stv[pi] = make_float4(v[pi][0], z[1], z[2], z[3]);
           }
+          store_R_pair(sb, e, v[0], v[1]);
         }
       } else if (s < L) {
         // ---- hidden layer s forward --------------------------------------------------------
@@ -481,14 +494,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         tmem_ld_wait();
         if (e.active) {
 #pragma unroll
+          float v[PPT][4];
+#pragma unroll
           for (int pi = 0; pi < PPT; ++pi) {
             z[pi][0] += bias[s];
-            float v[4], hi[4], lo[4];
-            jet_fwd(z[pi], v);
-            stv[pi] = make_float4(v[0], z[pi][1], z[pi][2], z[pi][3]);
-            split4(v, hi, lo);
-            store_R(sb, e, pi, hi, lo);
+            jet_fwd(z[pi], v[pi]);
+            stv[pi] = make_float4(v[pi][0], z[pi][1], z[pi][2], z[pi][3]);
           }
+          store_R_pair(sb, e, v[0], v[1]);
         }
       } else if (s == L) {
         // ---- output layer: gather, residuals, adjoint seeds ---------------------------------
@@ -515,10 +528,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         if (TRAIN && part != 1) {
           if (e.active) {
             float sb0 = 0.f;
+            float zb2[PPT][4];
 #pragma unroll
             for (int pi = 0; pi < PPT; ++pi) {
               const float4* ov4 = reinterpret_cast<const float4*>(misc->ov[slot][e.sub * PPT + pi]);
-              float ab[4], zb[4], act[4], hi[4], lo[4];
+              float ab[4], act[4];
+              float* zb = zb2[pi];
               float4 ovs[4];
 #pragma unroll
               for (int st = 0; st < 4; ++st) {
@@ -534,11 +549,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
                 gwl[2] = fmaf(ovs[st].z, act[st], gwl[2]);
               }
               sb0 += zb[0];
-              if (L >= 2) {
-                split4(zb, hi, lo);
-                store_R(sb, e, pi, hi, lo);
-              }
             }
+            if (L >= 2) store_R_pair(sb, e, zb2[0], zb2[1]);
             gb[L - 1] += sb0;
           }
         }
@@ -550,23 +562,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         tmem_ld_wait();
         if (e.active) {
           float sb0 = 0.f;
+          float zb2[PPT][4];
 #pragma unroll
           for (int pi = 0; pi < PPT; ++pi) {
-            float zb[4], hi[4], lo[4];
-            zbar_from(st_l[pi], ab[pi], zb);
-            sb0 += zb[0];
-            if (l >= 1) {
-              split4(zb, hi, lo);
-              // the weight-gradient MMAs of this stage still read both image pairs of the slot: wait for them
-              if (pi == 0) { mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u); }
-              store_R(sb, e, pi, hi, lo);
-              float av[4];
-              act_from_stash(st_lm1[pi], av);
-              split4(av, hi, lo);
-              store_R(sb + 2 * RB, e, pi, hi, lo);
-            } else {
-              gw0x += fmaf(zb[0], xv[pi], zb[1]); gw0y += fmaf(zb[0], yv[pi], zb[2]);
-            }
+            zbar_from(st_l[pi], ab[pi], zb2[pi]);
+            sb0 += zb2[pi][0];
+            if (l == 0) { gw0x += fmaf(zb2[pi][0], xv[pi], zb2[pi][1]); gw0y += fmaf(zb2[pi][0], yv[pi], zb2[pi][2]); }
+          }
+          if (l >= 1) {
+            float av[PPT][4];
+#pragma unroll
+            for (int pi = 0; pi < PPT; ++pi) act_from_stash(st_lm1[pi], av[pi]);
+            // the weight-gradient MMAs of this stage still read both image pairs of the slot: wait for them
+            mbar_wait(&misc->wdone[slot], (wdphases >> slot) & 1u);
+            store_R_pair(sb, e, zb2[0], zb2[1]);
+            store_R_pair(sb + 2 * RB, e, av[0], av[1]);
           }
           gb[l] += sb0;
         }
