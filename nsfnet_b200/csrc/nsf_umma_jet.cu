@@ -116,10 +116,16 @@ __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, f
 __host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t layout_type) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29); }
 
 // ---- issuer: the MMAs of stage s for one slot (executed by the whole issuer warp, see mma_tf32_elect2) ----
+// Every descriptor is  sb4 + <compile-time constant>  with sb4 = (shared window base) >> 4 held in ONE uniform register
+// (the slot loop is unrolled): the descriptor set-up between "operands ready" and the first MMA used to be ~40
+// R2UR / uniform instructions (~170 cycles with the tensor pipe idle).  Shared addresses are < 2^18, so the 14-bit
+// address field never carries into the LBO field.
+__host__ __device__ constexpr uint32_t lbo_field(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
+
 template <int L>
-__device__ __forceinline__ void issue_main(uint32_t smem_base, uint32_t tmem, int s, int slot, int wbuf, uint32_t leader) {
-  const uint32_t wa = smem_base + (uint32_t)wbuf * WBUF;
-  const uint32_t sb = smem_base + OFF_SLOT + (uint32_t)slot * SLOT;
+__device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, int slot, uint32_t wbuf, uint32_t leader) {
+  const uint32_t wa4 = sb4 + (wbuf ? (WBUF >> 4) : 0u);
+  const uint32_t r4 = sb4 + (uint32_t)((OFF_SLOT + slot * SLOT) >> 4);
   const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
   {  // forward (s <= L) or dgrad (s > L): D[128, 4P] = Wimg[128, 80] * R[4P, 80]^T
     // The tensor core truncates when it adds into the fp32 accumulator (measured: -2e-8 relative per MMA for
@@ -128,8 +134,8 @@ __device__ __forceinline__ void issue_main(uint32_t smem_base, uint32_t tmem, in
     // The output layer (s = L) has 3 real rows: M = 64 halves the operand fetch of its MMAs.
     const uint32_t idesc = (s == L) ? idesc_tf32(64, NCOL, 0, 1) : idesc_tf32(128, NCOL, 0, 1);
     constexpr uint32_t AHI = desc_hi(W_SBO), BHI = desc_hi_t(R_ATOM, 1);
-    const uint32_t ah0 = desc_lo(wa, 128), al0 = desc_lo(wa + IMG, 128);
-    const uint32_t bh0 = desc_lo(sb, 1024), bl0 = desc_lo(sb + RB, 1024);
+    const uint32_t ah0 = wa4 + lbo_field(128), al0 = ah0 + (IMG >> 4);
+    const uint32_t bh0 = r4 + lbo_field(1024), bl0 = bh0 + (RB >> 4);
 #pragma unroll
     for (int ks = 0; ks < KP / 8; ++ks) {
       const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
@@ -144,8 +150,8 @@ __device__ __forceinline__ void issue_main(uint32_t smem_base, uint32_t tmem, in
   }
 }
 template <int L>
-__device__ __forceinline__ void issue_wgrad(uint32_t smem_base, uint32_t tmem, int s, int slot, bool zero_dw, uint32_t leader) {
-  const uint32_t sb = smem_base + OFF_SLOT + (uint32_t)slot * SLOT;
+__device__ __forceinline__ void issue_wgrad(uint32_t sb4, uint32_t tmem, int s, int slot, bool zero_dw, uint32_t leader) {
+  const uint32_t r4 = sb4 + (uint32_t)((OFF_SLOT + slot * SLOT) >> 4);
   {  // wgrad: dW_l[128, 80] += Zbar[128, 4P] * Act[80, 4P]^T, contraction over n = 4p + s.  Both operands are the row-per-neuron
      // images the epilogue already wrote for the MN-major reads, now read K-MAJOR with the same descriptor layout type 1
      // (measured, scripts/probe_mma.cu: rows 128 B apart in groups of 4, SBO between groups, a K step is one 32-byte chunk).
@@ -153,8 +159,8 @@ __device__ __forceinline__ void issue_wgrad(uint32_t smem_base, uint32_t tmem, i
     const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
     const uint32_t dw_col = tmem + (uint32_t)((l - 1) * NW);
     constexpr uint32_t RHI = desc_hi_t(R_ATOM, 1);
-    const uint32_t ah0 = desc_lo(sb, 0), al0 = desc_lo(sb + RB, 0);
-    const uint32_t bh0 = desc_lo(sb + 2 * RB, 0), bl0 = desc_lo(sb + 3 * RB, 0);
+    const uint32_t ah0 = r4, al0 = r4 + (RB >> 4);
+    const uint32_t bh0 = r4 + ((2 * RB) >> 4), bl0 = r4 + ((3 * RB) >> 4);
 #pragma unroll
     for (int ks = 0; ks < NCOL / 8; ++ks) {
       const uint32_t d = ks * (32 >> 4);
@@ -290,8 +296,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 #pragma unroll 1
       for (int s = 1; s < NSTAGE; ++s) {
         const uint32_t b = stage_ctr & 1u;
-#pragma unroll 1
-        for (int slot = 0; slot < NS; ++slot) {
+#pragma unroll
+        for (int slot = 0; slot < NS; ++slot) {     // unrolled: the slot's operand descriptors are constants + smem_base
           long long t0 = 0, t1 = 0;
           if (DBG) t0 = clock64();
           mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u); rphases ^= 1u << slot;
@@ -305,11 +311,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
           // dgrad first: the epilogue of the next stage only needs its result; the weight-gradient MMAs get their own
           // completion barrier (they read the C images, which that epilogue rewrites last)
-          issue_main<L>(smem_base, tmem, s, slot, (int)b, leader);
+          issue_main<L>(smem_base >> 4, tmem, s, slot, b, leader);
           mma_commit_elect(&misc->mbar[slot], leader);
           if (slot == NS - 1) mma_commit_elect(&misc->wfree[b], leader);
           if (s > L) {
-            issue_wgrad<L>(smem_base, tmem, s, slot, (pr % FLUSH) == 0 && slot == 0, leader);
+            issue_wgrad<L>(smem_base >> 4, tmem, s, slot, (pr % FLUSH) == 0 && slot == 0, leader);
             mma_commit_elect(&misc->wdone[slot], leader);
           }
           __syncwarp();
