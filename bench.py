@@ -107,7 +107,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "collocation_pts_per_s (residual + weight gradient)", "value": pts_s, "unit": "pts/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n_f_override=n_f),
+            "config": dict(workload_config(args, n_f_override=n_f), kernel_path="reference algorithm on the host cores (torch autograd, oracle/autograd_port.py)",
+                           l2="n/a (CPU run)", sample_of=f"the {args.n_f}-point workload: {n_f} collocation points per step"),
             "cpu_baseline": {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": "port",
                              "sample": f"{n_f} collocation pts + 2052 boundary pts per step, full Adam step (N_f=1e6 does not fit host memory for the reference's retained graph)"},
             "e2e": {"value": pts_s, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
