@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       if (is_rev && e.active) {
 #pragma unroll
         for (int pi = 0; pi < PPT; ++pi) {
-          if (part != 1) st_l[pi] = __ldcs(st_slot + lrev * (P * KP) + pi * KP);
-          if (lrev >= 1 && part != 2) st_lm1[pi] = __ldcs(st_slot + (lrev - 1) * (P * KP) + pi * KP);
+          if (part != 1) st_l[pi] = __ldcg(st_slot + lrev * (P * KP) + pi * KP);
+          if (lrev >= 1 && part != 2) st_lm1[pi] = __ldcg(st_slot + (lrev - 1) * (P * KP) + pi * KP);
         }
       }
       float4 stv[PPT];                                                  // (t, zx, zy, z_lap) of a forward stage, stashed after the hand-over
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       if (TRAIN && s < L && e.active) {
         // the stash stores go to L2 after the hand-over: the proxy fence above would wait for them
 #pragma unroll
-        for (int pi = 0; pi < PPT; ++pi) __stcs(st_slot + s * (P * KP) + pi * KP, stv[pi]);
+        for (int pi = 0; pi < PPT; ++pi) __stcg(st_slot + s * (P * KP) + pi * KP, stv[pi]);
       }
       if (DBG) { t1 = clock64(); tcnt[cls + 2] += t1 - t0; tcnt[cls + 4] += 1; }
     };
