@@ -123,7 +123,7 @@ __host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t la
 __host__ __device__ constexpr uint32_t lbo_field(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
 
 template <int L>
-__device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, int slot, uint32_t wbuf, uint32_t leader) {
+__device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, int slot, uint32_t wbuf, uint32_t leader, int half) {
   const uint32_t wa4 = sb4 + (wbuf ? (WBUF >> 4) : 0u);
   const uint32_t r4 = sb4 + (uint32_t)((OFF_SLOT + slot * SLOT) >> 4);
   const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
@@ -136,16 +136,19 @@ __device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, i
     constexpr uint32_t AHI = desc_hi(W_SBO), BHI = desc_hi_t(R_ATOM, 1);
     const uint32_t ah0 = wa4 + lbo_field(128), al0 = ah0 + (IMG >> 4);
     const uint32_t bh0 = r4 + lbo_field(1024), bl0 = bh0 + (RB >> 4);
+    if (half == 0) {
 #pragma unroll
-    for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
-      mma_tf32_elect2(d_col, al0 + da, AHI, bh0 + db, BHI, idesc, ks > 0, leader);
-      mma_tf32_elect2(d_col, ah0 + da, AHI, bl0 + db, BHI, idesc, 1, leader);
-    }
+      for (int ks = 0; ks < KP / 8; ++ks) {
+        const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
+        mma_tf32_elect2(d_col, al0 + da, AHI, bh0 + db, BHI, idesc, ks > 0, leader);
+        mma_tf32_elect2(d_col, ah0 + da, AHI, bl0 + db, BHI, idesc, 1, leader);
+      }
+    } else {
 #pragma unroll
-    for (int ks = 0; ks < KP / 8; ++ks) {
-      const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
-      mma_tf32_elect2(d_col, ah0 + da, AHI, bh0 + db, BHI, idesc, 1, leader);
+      for (int ks = 0; ks < KP / 8; ++ks) {
+        const uint32_t da = ks * (256 >> 4), db = ks * ((2 * R_ATOM) >> 4);
+        mma_tf32_elect2(d_col, ah0 + da, AHI, bh0 + db, BHI, idesc, 1, leader);
+      }
     }
   }
 }
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     // issues the MMAs and the commits.
     const uint32_t leader = elect_one();
     uint32_t rphases = 0;                  // bit = slot: parity to wait for
+    bool pre_ok = false;                   // the next slot's `ready` phase was already seen complete
     uint32_t stage_ctr = 0;                // MMA stages issued so far (selects the weight buffer)
     long long icnt[5] = {0, 0, 0, 0, 0};   // -, issue, operand (+ weight) wait, -, stage-slots
     long long swait[2 * MAXL];             // operand wait per stage (diagnostic rows of the two non-epilogue warps)
@@ -300,18 +304,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
         for (int slot = 0; slot < NS; ++slot) {     // unrolled: the slot's operand descriptors are constants + smem_base
           long long t0 = 0, t1 = 0;
           if (DBG) t0 = clock64();
-          mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u); rphases ^= 1u << slot;
+          const bool fenced = pre_ok;
+          if (!pre_ok) mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u);
+          rphases ^= 1u << slot;
           if (DBG) {
             t1 = clock64(); icnt[2] += t1 - t0;
 #pragma unroll
             for (int i = 1; i < 2 * MAXL; ++i) if (i == s) swait[i] += t1 - t0;
             t0 = t1;
           }
-          tc_fence_after();
+          if (!fenced) tc_fence_after();
           if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
           // dgrad first: the epilogue of the next stage only needs its result; the weight-gradient MMAs get their own
           // completion barrier (they read the C images, which that epilogue rewrites last)
-          issue_main<L>(smem_base >> 4, tmem, s, slot, b, leader);
+          issue_main<L>(smem_base >> 4, tmem, s, slot, b, leader, 0);
+          // probe the next slot's operands while this slot's MMAs queue up: a blocking poll after the last MMA costs
+          // the pipe its ~4-deep queue (150-200 cycles per stage and slot, round-1 cycle counters)
+          {
+            const int nslot = (slot + 1) % NS;
+            pre_ok = mbar_test_wait(&misc->ready[nslot], (rphases >> nslot) & 1u);
+            if (pre_ok) tc_fence_after();     // the fence of the next slot, overlapped with this slot's queued MMAs
+          }
+          issue_main<L>(smem_base >> 4, tmem, s, slot, b, leader, 1);
           mma_commit_elect(&misc->mbar[slot], leader);
           if (slot == NS - 1) mma_commit_elect(&misc->wfree[b], leader);
           if (s > L) {
