@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--cpu-n-f", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the 120 000-point Adam-iteration measurement")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 tile-major, 3 tcgen05 layer-major")
     ap.add_argument("--nt", type=int, default=0, help="tiles per super-batch of the layer-major kernel (0 = default)")
     args = ap.parse_args()
@@ -178,11 +179,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     n = args.n_f
     x = torch.rand(n, device=dev, generator=g); y = torch.rand(n, device=dev, generator=g)
-    ws_save, rk_save = P.world_size, P.rank
-    P.world_size, P.rank = 1, 0
-    P.set_eq_training_data((x, y))
-    P.world_size, P.rank = ws_save, rk_save
-    P._n_f_global = n * world
+    P.set_eq_training_shard((x, y), n_global=n * world)
     if args.workload == "ev":
         P.freeze_evm_net(0)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -223,25 +220,63 @@ def main():
     value = n * world / (ms_per_step * 1e-3)
 
     # ---- metric (ii): full Adam iterations (loss, backward, optimizer) ---------------------------
+    # (a) the reference's own loop body on the drop-in classes: fwd_computing_loss_2d + loss.backward() + torch.optim.Adam
+    # (b) the fused iteration: nsf_step + device-resident Adam replayed as one CUDA graph (one process;
+    #     launched eagerly under data parallelism because of the NCCL all-reduce in the middle)
     def adam_iter():
         loss, _ = P.fwd_computing_loss_2d()
         P.opt.zero_grad()
         loss.backward()
         P.opt.step()
         return loss
-    for _ in range(3):
-        adam_iter()
-    sync_all()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        adam_iter()
-    t1.record()
-    sync_all()
-    adam_ms = torch.tensor([t0.elapsed_time(t1) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(adam_ms, op=dist.ReduceOp.MAX)
-    adam_steps_s = 1e3 / float(adam_ms.item())
+
+    def time_iters(fn, steps):
+        for _ in range(3):
+            fn()
+        sync_all()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        sync_all()
+        wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+        ms = torch.tensor([max(t0.elapsed_time(t1) / steps, wall_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return 1e3 / float(ms.item())
+
+    def fused_on(S):
+        S.enable_fused_step(True)
+        if args.workload == "ev":
+            S.freeze_evm_net(0)
+        else:
+            S._adam_reset()
+        S._adam_set_lr(1e-3)
+
+    P._ctx.set_timing(False)
+    adam_torch_steps_s = time_iters(adam_iter, args.steps)
+    fused_on(P)
+    adam_steps_s = time_iters(P._fused_step_replayable, args.steps)
+    P.enable_fused_step(False)
+    small = None
+    if world == 1 and not args.no_small:
+        # the shipped configuration's point count (ev-NSFnet/configs/production.yaml: N_f = 120 000), where the iteration is
+        # launch / Python bound rather than kernel bound
+        n_s = 120_000
+        x_s = torch.rand(n_s, device=dev, generator=g); y_s = torch.rand(n_s, device=dev, generator=g)
+        P.set_eq_training_shard((x_s, y_s), n_global=n_s)
+        if args.workload == "ev":
+            P.freeze_evm_net(0)
+        a = time_iters(adam_iter, 200)
+        fused_on(P)
+        b = time_iters(P._fused_step_replayable, 200)
+        P.enable_fused_step(False)
+        small = {"n_f": n_s, "adam_steps_per_s_torch_optim_loop": a, "adam_steps_per_s_fused_graph": b}
+        P.set_eq_training_shard((x, y), n_global=n * world)
+        if args.workload == "ev":
+            P.freeze_evm_net(0)
 
     # ---- e2e: public API with HOST buffers (pinned), H2D of the points + D2H of the loss every step
     e2e = None
@@ -249,16 +284,12 @@ def main():
         hx = torch.rand(n, 1).pin_memory(); hy = torch.rand(n, 1).pin_memory()
 
         def e2e_iter():
-            P.set_eq_training_data((hx, hy))          # H2D of this step's points (+ the reference's init_vis_t)
-            P._n_f_global = n * world
+            P.set_eq_training_shard((hx, hy), n_global=n * world)   # H2D of this step's points (+ the reference's init_vis_t)
             loss, _ = P.fwd_computing_loss_2d()
             P.opt.zero_grad()
             loss.backward()
             return float(loss)                          # D2H of the result
         P.verbose = False
-        P.world_size, P.rank = ws_save, rk_save
-        shard = P._shard
-        P._shard = lambda total: (0, total)             # the host buffers ARE this rank's shard
         for _ in range(2):
             e2e_iter()
         sync_all()
@@ -267,12 +298,11 @@ def main():
             e2e_iter()
         sync_all()
         e2e_s = (time.perf_counter() - w0) / args.steps
-        P._shard = shard
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": n * world / float(t.item()), "unit": "pts/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4,
-               "ms_per_step": float(t.item()) * 1e3, "api": "set_eq_training_data(pinned host x,y) + fwd_computing_loss_2d() + loss.backward() + float(loss)"}
+               "ms_per_step": float(t.item()) * 1e3, "api": "set_eq_training_shard(pinned host x,y) + fwd_computing_loss_2d() + loss.backward() + float(loss)"}
 
     if rank != 0:
         if world > 1:
@@ -290,7 +320,10 @@ def main():
     line = {"metric": "collocation_pts_per_s (residual + weight gradient)", "value": value, "unit": "pts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "adam_steps_per_s": adam_steps_s,
+            "adam_steps_per_s": adam_steps_s, "adam_steps_per_s_torch_optim_loop": adam_torch_steps_s,
+            "adam_iteration": "nsf_step + device-resident Adam (nsf_adam_dev), one CUDA graph replay per iteration" if world == 1
+                              else "nsf_step + NCCL all-reduce + device-resident Adam (nsf_adam_dev), launched eagerly",
+            "adam_small_batch": small,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get((args.workload, info["path"], n)),
                          "kernel": "collocation jet step (fwd jet + residuals + reverse)", "kernel_ms": k_ms,

@@ -171,6 +171,44 @@ int nsf_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq
              float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
              void* stream);
 
+/* Device-resident Adam state: hyper-parameters and the step counter live in device memory, so a training iteration
+ * (nsf_step + nsf_adam_dev [+ nsf_adam_dev for the EVM net] + nsf_adam_tick) has no host-side scalar that changes from
+ * step to step and ONE captured CUDA graph replays it ("next" row f.1: the reference's per-iteration Python of
+ * ev :456-472).  `step` = number of updates already applied; the update uses t = step + 1 for the bias corrections.
+ * A fresh `torch.optim.Adam` (what freeze_evm_net / defreeze_evm_net create, ev :489-511) = zeroed moments + step = 0;
+ * a new stage learning rate (ev train :383-388) = a 4-byte write to `lr`. */
+typedef struct {
+  float lr, beta1, beta2, eps;
+  float grad_scale; /* multiplies the gradient first (1.0; 1/W reproduces the reference's DDP quirk) */
+  int32_t step;
+  int32_t reserved[2];
+} NsfAdamDev;
+
+/* One Adam update of a flat buffer with the DEVICE-resident state (does not advance state->step). */
+int nsf_adam_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 NsfAdamDev* state, void* stream);
+/* state->step += 1 on the device, after every buffer of the iteration has been updated. */
+int nsf_adam_tick(NsfAdamDev* state, void* stream);
+
+/* On-device point layer ("next" row f.2; the reference's pure-Python LHSample + cKDTree, tools.py:30-57 and
+ * cavity_data.py:96-130, take hours at 1e6 points).
+ *
+ * nsf_lhs_points: rows [first, first+count) of a Latin-hypercube design of n_total points in
+ *   [x_min,x_max] x [y_min,y_max]: per dimension every 1/n_total stratum holds exactly one point, at a uniform
+ *   position inside it, strata assigned by an independent pseudo-random permutation per dimension (a keyed Feistel
+ *   network, so any row range of the SAME design can be produced by any rank without communication).
+ * nsf_wall_distance: distance of every point to the nearest of the n_b discrete boundary points
+ *   (cKDTree(pts_bc).query, cavity_data.py:118-121; also the sort key of tools.py:68-83).
+ * nsf_sdf_weights: w = w_min + (1-w_min) exp(-decay d), UNNORMALISED (cavity_data.py:122-127 clamps included);
+ *   when w_sum != NULL the sum of the weights is ADDED to *w_sum (device double, caller zeroes it), so the caller
+ *   divides by the mean over the GLOBAL point set (all-reduce of one double under data parallelism). */
+int nsf_lhs_points(int64_t n_total, int64_t first, int64_t count, uint32_t seed, float x_min, float x_max,
+                   float y_min, float y_max, float* x_out, float* y_out, void* stream);
+int nsf_wall_distance(const float* x, const float* y, int64_t n, const float* xb, const float* yb, int32_t n_b,
+                      float* dist_out, void* stream);
+int nsf_sdf_weights(const float* x, const float* y, int64_t n, const float* xb, const float* yb, int32_t n_b,
+                    float min_weight, float decay, float* w_out, double* w_sum, void* stream);
+
 /* Debug / validation: runs one tcgen05 TF32 GEMM D[128,n] = A[128,k] * B[n,k]^T with the same
  * shared-memory descriptors the jet kernel uses (variant selects operand majors / 3xTF32 split)
  * so tests can check the descriptor encodings against a CPU product. */

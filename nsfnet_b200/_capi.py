@@ -21,7 +21,8 @@ NSF_LOSS_SLOTS = 16
 
 EXPORTS = ["nsf_abi_version", "nsf_last_error", "nsf_create", "nsf_destroy", "nsf_set_path", "nsf_get_info",
            "nsf_set_timing", "nsf_last_kernel_ms", "nsf_get_stage_cycles", "nsf_set_tiles_per_batch",
-           "nsf_step", "nsf_residuals", "nsf_forward", "nsf_adam", "nsf_selftest_umma"]
+           "nsf_step", "nsf_residuals", "nsf_forward", "nsf_adam", "nsf_selftest_umma",
+           "nsf_adam_dev", "nsf_adam_tick", "nsf_lhs_points", "nsf_wall_distance", "nsf_sdf_weights"]
 
 
 class NsfNetDesc(C.Structure):
@@ -37,6 +38,12 @@ class NsfPhysics(C.Structure):
 class NsfDataBlock(C.Structure):
     _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("p", C.c_void_p),
                 ("n", C.c_int64), ("cu", C.c_float), ("cv", C.c_float), ("cp", C.c_float), ("reserved", C.c_int32)]
+
+
+class NsfAdamDev(C.Structure):
+    """Device-resident Adam state (32 bytes); host mirror used to initialise the device copy."""
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("grad_scale", C.c_float), ("step", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class NsfError(RuntimeError):
@@ -77,6 +84,16 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nsf_forward.argtypes = [vp, i32, vp, vp, vp, i64, vp, vp]
     lib.nsf_adam.restype = C.c_int
     lib.nsf_adam.argtypes = [vp, vp, vp, vp, i64, f, f, f, f, i64, f, vp]
+    lib.nsf_adam_dev.restype = C.c_int
+    lib.nsf_adam_dev.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    lib.nsf_adam_tick.restype = C.c_int
+    lib.nsf_adam_tick.argtypes = [vp, vp]
+    lib.nsf_lhs_points.restype = C.c_int
+    lib.nsf_lhs_points.argtypes = [i64, i64, i64, C.c_uint32, f, f, f, f, vp, vp, vp]
+    lib.nsf_wall_distance.restype = C.c_int
+    lib.nsf_wall_distance.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp]
+    lib.nsf_sdf_weights.restype = C.c_int
+    lib.nsf_sdf_weights.argtypes = [vp, vp, i64, vp, vp, i32, f, f, vp, vp, vp]
     lib.nsf_selftest_umma.restype = C.c_int
     lib.nsf_selftest_umma.argtypes = [C.c_int, i32, vp, vp, vp, i32, i32, vp]
     return lib

@@ -113,3 +113,93 @@ class DataLoader:
         if self.coord_transform:
             x, y = x * 2.0 - 1.0, y * 2.0 - 1.0
         return tuple(a.reshape(-1, 1) for a in (x, y, u, v, p))
+
+
+# ---- on-device point layer -------------------------------------------------------------------
+# The same point sets produced by libnsf_b200 on the GPU (include/nsf_b200.h: nsf_lhs_points / nsf_wall_distance /
+# nsf_sdf_weights): 1e6 points take milliseconds instead of the hours of the reference's per-sample Python loops, and
+# under data parallelism every rank generates only its own rows of the one global Latin-hypercube design.
+
+def _lib_stream(device):
+    import torch
+    from . import _capi
+    return _capi.load(), torch.cuda.current_stream(device).cuda_stream
+
+
+def lhs_sample_device(n_total, device, seed=0, bounds=((0.0, 1.0), (0.0, 1.0)), first=0, count=None):
+    """Rows [first, first+count) of a Latin-hypercube design of ``n_total`` points -> (x, y) fp32 device tensors."""
+    import torch
+    from . import _capi
+    count = n_total - first if count is None else count
+    lib, st = _lib_stream(device)
+    x = torch.empty(count, dtype=torch.float32, device=device)
+    y = torch.empty(count, dtype=torch.float32, device=device)
+    (x0, x1), (y0, y1) = bounds
+    _capi.check(lib, lib.nsf_lhs_points(int(n_total), int(first), int(count), int(seed) & 0xFFFFFFFF, x0, x1, y0, y1,
+                                        x.data_ptr(), y.data_ptr(), st))
+    return x, y
+
+
+def wall_distance_device(x, y, xb, yb):
+    """Distance to the nearest discrete boundary point (cKDTree.query of cavity_data.py:118-121) for device tensors."""
+    import torch
+    from . import _capi
+    lib, st = _lib_stream(x.device)
+    d = torch.empty_like(x)
+    _capi.check(lib, lib.nsf_wall_distance(x.data_ptr(), y.data_ptr(), x.numel(), xb.data_ptr(), yb.data_ptr(), xb.numel(), d.data_ptr(), st))
+    return d
+
+
+def sdf_weights_device(x, y, xb, yb, min_weight=0.2, decay=5.0, distributed=False):
+    """SDF weights normalised to mean 1 over the GLOBAL point set (cavity_data.py:118-130; one all-reduce of
+    (sum, count) when ``distributed``)."""
+    import torch
+    import torch.distributed as dist
+    from . import _capi
+    lib, st = _lib_stream(x.device)
+    w = torch.empty_like(x)
+    acc = torch.zeros(2, dtype=torch.float64, device=x.device)
+    acc[1] = float(x.numel())
+    _capi.check(lib, lib.nsf_sdf_weights(x.data_ptr(), y.data_ptr(), x.numel(), xb.data_ptr(), yb.data_ptr(), xb.numel(),
+                                         float(min_weight), float(decay), w.data_ptr(), acc.data_ptr(), st))
+    if distributed:
+        dist.all_reduce(acc)
+    mean = acc[0] / acc[1]
+    return w * torch.where(mean > 0, 1.0 / mean, torch.ones_like(mean)).to(torch.float32)
+
+
+class DeviceDataLoader(DataLoader):
+    """``DataLoader`` whose collocation set lives on the GPU from the start.  ``loading_training_data`` returns THIS rank's
+    shard (rows ``shard_bounds`` of the global design, or the whole sorted set when ``sort_training_points``) as device
+    tensors for ``solver.set_eq_training_shard``."""
+
+    def __init__(self, device, rank=0, world_size=1, seed=0, **kw):
+        super().__init__(seed=seed, **kw)
+        self.device, self.rank, self.world_size, self.seed = device, rank, world_size, 0 if seed is None else int(seed)
+
+    def loading_training_data(self):
+        import torch
+        if self.pts_bc is None:
+            raise RuntimeError("need to load boundary data first!")
+        per = self.N_f // self.world_size
+        first = self.rank * per
+        count = per if self.rank < self.world_size - 1 else self.N_f - first
+        bounds = ((self.x_min, self.x_max), (self.y_min, self.y_max))
+        xb = torch.as_tensor(self.pts_bc[:, 0], dtype=torch.float32, device=self.device).contiguous()
+        yb = torch.as_tensor(self.pts_bc[:, 1], dtype=torch.float32, device=self.device).contiguous()
+        if self.sort_training_points:
+            # the reference sorts the GLOBAL set by wall distance and shards it in contiguous blocks (tools.py:68-83, ev :165-177)
+            x, y = lhs_sample_device(self.N_f, self.device, self.seed, bounds)
+            if self.coord_transform:
+                x, y = x * 2.0 - 1.0, y * 2.0 - 1.0
+            idx = torch.argsort(wall_distance_device(x, y, xb, yb), stable=True)[first:first + count]
+            x, y = x[idx].contiguous(), y[idx].contiguous()
+        else:
+            x, y = lhs_sample_device(self.N_f, self.device, self.seed, bounds, first, count)
+            if self.coord_transform:
+                x, y = x * 2.0 - 1.0, y * 2.0 - 1.0
+        self.sdf_weights = None
+        if self.sdf_enabled:
+            self.sdf_weights = sdf_weights_device(x, y, xb, yb, getattr(self.sdf_config, "min_weight", 0.2),
+                                                  getattr(self.sdf_config, "decay", 5.0), distributed=self.world_size > 1)
+        return x, y

@@ -53,16 +53,21 @@ class PysicsInformedNeuralNetwork(SolverBase):
         if not hasattr(self, "log_interval"):
             self.log_interval = 100
         self.freeze_evm_net(0)
+        fused = self._fused and loss_func == self.fwd_computing_loss_2d
         for epoch_id in range(num_epoch):
             self.global_step += 1
             if epoch_id != 0 and epoch_id % 10000 == 0:
                 self.defreeze_evm_net(epoch_id)
             if (epoch_id - 1) % 10000 == 0:
                 self.freeze_evm_net(epoch_id)
-            loss, losses = loss_func()
-            self.opt.zero_grad()
-            loss.backward()
-            self.opt.step()
+            if fused:
+                loss = self._fused_step_replayable()
+                losses = [self.loss_e, self.loss_b]
+            else:
+                loss, losses = loss_func()
+                self.opt.zero_grad()
+                loss.backward()
+                self.opt.step()
             if scheduler:
                 scheduler.step()
             interval = self.log_interval if self.log_interval > 0 else 100
@@ -76,12 +81,16 @@ class PysicsInformedNeuralNetwork(SolverBase):
             p.requires_grad = False
         self.opt = torch.optim.Adam([p for p in self.net.parameters() if p.requires_grad],
                                     lr=self.opt.param_groups[0]["lr"], weight_decay=0.0)
+        if self._fused:
+            self._adam_reset(); self._adam_set_lr(self.opt.param_groups[0]["lr"])
 
     def defreeze_evm_net(self, epoch_id):
         for p in self.net_1.parameters():
             p.requires_grad = True
         self.opt = torch.optim.Adam(list(self.net.parameters()) + list(self.net_1.parameters()),
                                     lr=self.opt.param_groups[0]["lr"], weight_decay=0.0)
+        if self._fused:
+            self._adam_reset(); self._adam_set_lr(self.opt.param_groups[0]["lr"])
 
     def _save_dir(self, directory, N_HLayer, N_neu, N_f):
         import numpy as np

@@ -46,11 +46,20 @@ class PysicsInformedNeuralNetwork(SolverBase):
         import time
         self._epoch_start_wall = time.time()
         epoch_id = 0
+        fused = self._fused and loss_func == self.fwd_computing_loss_2d
+        if fused:                      # ONE Adam for the whole run (NSFnet :76-79); only the learning rate follows the stage
+            if self._adam is None:
+                self._adam_reset()
+            self._adam_set_lr(self.opt.param_groups[0]["lr"])
         while epoch_id < num_epoch:
-            loss, losses = loss_func()
-            loss.backward()
-            self.opt.step()
-            self.opt.zero_grad()
+            if fused:
+                loss = self._fused_step_replayable()
+                losses = [self.loss_e, self.loss_b]
+            else:
+                loss, losses = loss_func()
+                loss.backward()
+                self.opt.step()
+                self.opt.zero_grad()
             if scheduler:
                 scheduler.step()
             if self.rank == 0 and epoch_id % getattr(self, "log_interval", 1000) == 0:

@@ -113,6 +113,10 @@ class SolverBase:
         self.ddp_compat = False
         self.store_residuals = True
         self.x_b = self.x_f = None
+        self._fused = False          # enable_fused_step(): device-resident Adam + CUDA-graph replay of the iteration
+        self._fused_graph = True
+        self._graphs = {}
+        self._adam = None
 
         self.net = self.initialize_NN(num_ins=num_ins, num_outs=num_outs, num_layers=layers, hidden_size=hidden_size).to(self.device)
         self.net_1 = None
@@ -187,6 +191,25 @@ class SolverBase:
             print(f"GPU {self.rank}: Processing {e - s} equation points out of {total} total")
         if self.HAS_EVM:
             self.init_vis_t()
+
+    def set_eq_training_shard(self, X, weights=None, n_global=None):
+        """Extension (no reference counterpart): THIS rank's collocation shard, already on the device or the host, plus
+        the global point count.  What every rank of a data-parallel run calls when its shard is generated in place
+        (nsfnet_b200.cavity_data.DeviceDataLoader) instead of slicing one W*N host array per rank (ev :165-177)."""
+        ws, rk = self.world_size, self.rank
+        self.world_size, self.rank = 1, 0
+        try:
+            self.set_eq_training_data(X, weights=weights)
+        finally:
+            self.world_size, self.rank = ws, rk
+        n_loc = self.x_f.numel()
+        if n_global is None:
+            n_global = n_loc
+            if self.is_distributed:
+                t = torch.tensor([n_loc], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t)
+                n_global = int(t.item())
+        self._n_f_global = int(n_global)
 
     def set_coordinate_transform(self, scale):
         if scale is None or scale <= 0:
@@ -386,6 +409,85 @@ class SolverBase:
         else:
             self.opt = torch.optim.Adam(params=self.net.parameters(), lr=lr)
         return self.solve_Adam(self.fwd_computing_loss_2d, num_epoch, batchsize, scheduler)
+
+    # ---- fused iteration ---------------------------------------------------
+    def enable_fused_step(self, enabled=True, graph=True):
+        """Extension: run ``solve_Adam`` as ``nsf_step`` + device-resident Adam (``nsf_adam_dev``; same update rule as
+        ``torch.optim.Adam``, including the fresh-optimizer resets of freeze / defreeze, ev :489-511) and replay the whole
+        iteration as ONE captured CUDA graph.  Semantics of the reference loop (ev :440-487, NSFnet :240-278) are kept:
+        same iteration order, logging and checkpoint cadence; ``self.opt`` still carries the learning rate."""
+        self._fused, self._fused_graph = bool(enabled), bool(graph)
+        self._graphs = {}
+
+    def _adam_reset(self):
+        """A new ``torch.optim.Adam``: zero moments, step 0 (betas (0.9, 0.999), eps 1e-8, ev :126-129)."""
+        n = self._n_main + self._n_evm
+        if self._adam is None:
+            self._adam = dict(m=torch.zeros(n, dtype=torch.float32, device=self.device),
+                              v=torch.zeros(n, dtype=torch.float32, device=self.device),
+                              state=torch.zeros(8, dtype=torch.float32, device=self.device))
+        self._adam["m"].zero_(); self._adam["v"].zero_()
+        st = self._adam["state"]
+        st.copy_(torch.tensor([0.0, 0.9, 0.999, 1e-8, 1.0, 0.0, 0.0, 0.0], dtype=torch.float32))
+        st.view(torch.int32)[5] = 0
+
+    def _adam_set_lr(self, lr):
+        self._adam["state"][0:1].fill_(float(lr))
+
+    def adam_step_count(self) -> int:
+        return int(self._adam["state"].view(torch.int32)[5].item()) if self._adam is not None else 0
+
+    def _fused_iteration(self):
+        """One training iteration on the current stream: loss + gradient, Adam on every trainable flat buffer, tick."""
+        loss = self._launch_step()
+        lib, A = self._lib, self._adam
+        st, strm = A["state"].data_ptr(), self._stream()
+        nm = self._n_main
+        _capi.check(lib, lib.nsf_adam_dev(self.net.flat_params().data_ptr(), self._buf.data_ptr(), A["m"].data_ptr(),
+                                          A["v"].data_ptr(), nm, st, strm))
+        if self.HAS_EVM and any(p.requires_grad for p in self.net_1.parameters()):
+            _capi.check(lib, lib.nsf_adam_dev(self.net_1.flat_params().data_ptr(), self._buf[nm:].data_ptr(), A["m"][nm:].data_ptr(),
+                                              A["v"][nm:].data_ptr(), self._n_evm, st, strm))
+        _capi.check(lib, lib.nsf_adam_tick(st, strm))
+        self.loss = loss
+        return loss
+
+    def _graph_key(self):
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        trainable = self.HAS_EVM and any(p.requires_grad for p in self.net_1.parameters())
+        return (ptr(self.x_f), ptr(self.y_f), self.x_f.numel(), ptr(self.eq_weights), ptr(self.x_b), ptr(self.vis_t_minus),
+                ptr(self.x_s), ptr(self.p_s), self.supervision_enabled, float(self.alpha_evm), float(self.alpha_b), float(self.alpha_e),
+                float(self.alpha_s), float(self.coord_scale), trainable, self.store_residuals, self._n_f_global,
+                ptr(self.net.flat_params()), ptr(self.net_1.flat_params()) if self.net_1 is not None else 0)
+
+    def _fused_step_replayable(self):
+        """Iteration through a captured graph when allowed (single process, timing hooks off), else eagerly.  The first call for
+        a configuration runs eagerly (it creates the library's workspaces) and captures afterwards."""
+        use_graph = self._fused_graph and not self.is_distributed
+        if not use_graph:
+            return self._fused_iteration()
+        key = self._graph_key()
+        ent = self._graphs.get(key)
+        if ent is None:
+            loss = self._fused_iteration()          # a real iteration, also the warm-up of everything the capture may not allocate
+            key = self._graph_key()                  # (vis_t_minus may have been allocated by it)
+            self._graphs[key] = "armed"
+            return loss
+        if ent == "armed":
+            if len(self._graphs) > 8:
+                self._graphs = {}
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                self._fused_iteration()
+            names = ["loss", "loss_e", "loss_b", "loss_s", "loss_eq1", "loss_eq2", "loss_eq3"] + (["loss_eq4"] if self.HAS_EVM else [])
+            ent = (g, {k: getattr(self, k) for k in names})
+            self._graphs[key] = ent
+        g, outs = ent
+        for k, v in outs.items():
+            setattr(self, k, v)
+        g.replay()
+        return self.loss
 
     def get_runtime_stats(self, epoch_id, num_epoch):
         now = time.time()

@@ -16,7 +16,7 @@ from nsfnet_b200 import _capi
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libnsf_emu.so")
-SRCS = [os.path.join(ROOT, "nsfnet_b200", "csrc", f) for f in ("nsf_ffma.cu", "nsf_capi.cu")]
+SRCS = [os.path.join(ROOT, "nsfnet_b200", "csrc", f) for f in ("nsf_ffma.cu", "nsf_capi.cu", "nsf_aux.cu")]
 DEPS = SRCS + [os.path.join(ROOT, "nsfnet_b200", "csrc", f) for f in ("nsf_ffma_body.h", "nsf_geom.h", "nsf_internal.h")] + \
     [os.path.join(ROOT, "include", "nsf_b200.h")]
 
