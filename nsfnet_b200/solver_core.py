@@ -509,7 +509,7 @@ class SolverBase:
         start = getattr(self, "_epoch_start_wall", now)
         it_s = (epoch_id + 1) / max(now - start, 1e-9)
         n_pts = (self.x_f.numel() if self.x_f is not None else 0) + (self.x_b.numel() if self.x_b is not None else 0)
-        msg = (f"[{self.current_stage}] epoch {epoch_id + 1}/{num_epoch} lr={lr:.2e} loss={float(loss):.4e} "
+        msg = (f"[{self.current_stage}] epoch {epoch_id + 1}/{num_epoch} lr={lr:.2e} loss={float(loss.detach()):.4e} "
                f"eq1={float(self.loss_eq1):.3e} eq2={float(self.loss_eq2):.3e} eq3={float(self.loss_eq3):.3e}")
         if self.HAS_EVM:
             st = self.get_runtime_stats(epoch_id, num_epoch)
@@ -575,3 +575,50 @@ class SolverBase:
         if self.net_1 is not None:
             torch.save({k: v.detach().clone() for k, v in self.net_1.state_dict().items()}, out + filename + "_evm")
         return out
+
+    # ---- full training state ------------------------------------------------
+    def save_checkpoint(self, path):
+        """Extension: everything a bit-exact resume needs.  ``save`` (above) writes the reference's weights-only ``.pth``
+        files (ev :742-759); the reference forgets the optimizer moments, the step counters and the lagged viscosity
+        ``vis_t_minus``, so a run resumed from them restarts Adam and takes its first step with ``vis_t = vis_t0``."""
+        ck = {"format": "nsfnet_b200.checkpoint.v1",
+              "net": {k: v.detach().clone() for k, v in self.net.state_dict().items()},
+              "net_1": {k: v.detach().clone() for k, v in self.net_1.state_dict().items()} if self.net_1 is not None else None,
+              "evm_trainable": [bool(p.requires_grad) for p in self.net_1.parameters()] if self.net_1 is not None else None,
+              "opt": self.opt.state_dict() if self.opt is not None else None,
+              "fused_adam": {k: v.detach().clone() for k, v in self._adam.items()} if self._adam is not None else None,
+              "vis_t_minus": self.vis_t_minus.detach().clone() if self.vis_t_minus is not None else None,
+              "global_step": int(self.global_step), "alpha_evm": float(self.alpha_evm), "current_stage": self.current_stage,
+              "Re": float(self.Re), "n_f_local": int(self.x_f.numel()) if self.x_f is not None else 0}
+        d = os.path.dirname(os.path.abspath(path))
+        os.makedirs(d, exist_ok=True)
+        torch.save(ck, path)
+        return path
+
+    def load_checkpoint(self, path):
+        """Restore ``save_checkpoint`` state into this solver (same network shapes; the point sets are set by the caller as
+        usual, BEFORE this call, so that the saved lag state replaces the one ``set_eq_training_data`` initialises)."""
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        if ck.get("format") != "nsfnet_b200.checkpoint.v1":
+            raise ValueError(f"{path} is not a nsfnet_b200 checkpoint")
+        self.net.load_state_dict(ck["net"])
+        if self.net_1 is not None and ck["net_1"] is not None:
+            self.net_1.load_state_dict(ck["net_1"])
+            for p, r in zip(self.net_1.parameters(), ck["evm_trainable"]):
+                p.requires_grad = r
+        if ck["opt"] is not None:
+            params = self._trainable()
+            self.opt = torch.optim.Adam(params, lr=ck["opt"]["param_groups"][0]["lr"], weight_decay=0.0)
+            self.opt.load_state_dict(ck["opt"])
+        if ck["fused_adam"] is not None:
+            if self._adam is None:
+                self._adam_reset()
+            for k, v in ck["fused_adam"].items():
+                self._adam[k].copy_(v)
+        if ck["vis_t_minus"] is not None and self.x_f is not None and ck["vis_t_minus"].numel() == self.x_f.numel():
+            self.vis_t_minus = ck["vis_t_minus"].to(self.device).clone()
+        self.global_step = ck["global_step"]
+        self.alpha_evm = ck["alpha_evm"]
+        self.current_stage = ck["current_stage"]
+        self._graphs = {}
+        return ck

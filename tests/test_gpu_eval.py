@@ -1,0 +1,111 @@
+"""SURVEY 8f rows 3-4 / BASELINE config 4 on the GPU: value-only inference on the 385 x 385 grid of
+cavity_Re4000_384_Uniform.mat (148 225 points) against the torch module, the reference's error norms with NaN-masked
+pressure (ev :684-688), the .mat result writer (ev :723-740), the reference's weights-only checkpoints (ev :742-759) and
+the full-state checkpoint a bit-exact resume needs."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jet_numpy as J
+
+pytestmark = pytest.mark.gpu
+
+
+def _solver(seed=2, n_f=2000):
+    import torch
+    from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+    torch.manual_seed(seed)
+    P = PysicsInformedNeuralNetwork(Re=4000, layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=n_f, alpha_evm=0.03,
+                                    bc_weight=10, eq_weight=1, supervised_data_weight=0.0)
+    with torch.no_grad():      # leave the near-linear init regime
+        P.net.flat_params().mul_(2.0)
+    rng = np.random.default_rng(0)
+    xb, yb, ub, vb = J.cavity_boundary(65)
+    P.set_boundary_data((xb, yb, ub, vb))
+    P.set_eq_training_data((rng.random(n_f).astype(np.float32), rng.random(n_f).astype(np.float32)))
+    P.log_interval = 10 ** 9; P.checkpoints = False; P.verbose = False
+    return P
+
+
+def test_grid_inference_error_norms_and_result_file(tmp_path):
+    import scipy.io
+    import torch
+    P = _solver()
+    s = np.linspace(0.0, 1.0, 385)
+    X, Y = np.meshgrid(s, s)
+    x, y = X.reshape(-1, 1), Y.reshape(-1, 1)
+    assert x.shape[0] == 148225
+    u, v, p, e = P.neural_net_u(torch.as_tensor(x), torch.as_tensor(y))
+    assert u.shape == (148225,) and p.shape == (148225, 1) and e.shape == (148225, 1)
+    with torch.no_grad():
+        xy = torch.as_tensor(np.hstack([x, y]), dtype=torch.float64, device="cuda")
+        ref = P.net.double()(xy)
+        P.net.float(); P.net.flatten_()
+        ref1 = P.net_1.double()(xy)
+        P.net_1.float(); P.net_1.flatten_()
+    for got, want in ((u, ref[:, 0]), (v, ref[:, 1]), (p[:, 0], ref[:, 2]), (e[:, 0], ref1[:, 0])):
+        r = (got.double() - want).norm() / want.norm()
+        assert r.item() < 1e-5, r.item()
+    # "DNS" fields = the net's own output plus a known perturbation, pressure with NaN holes (the 384 file has them)
+    rng = np.random.default_rng(1)
+    u_t = ref[:, 0].cpu().numpy().reshape(-1, 1) * 1.01
+    v_t = ref[:, 1].cpu().numpy().reshape(-1, 1) + 0.003
+    p_t = ref[:, 2].cpu().numpy().reshape(-1, 1) * 0.98
+    holes = rng.random(p_t.shape) < 0.05
+    p_t[holes] = np.nan
+    eu, ev_, ep = P.evaluate(x, y, u_t, v_t, p_t)
+    up, vp, pp = [a.double().cpu().numpy().reshape(-1, 1) for a in (u, v, p)]
+    m = ~np.isnan(p_t)
+    assert abs(eu - 100 * np.linalg.norm(u_t - up) / np.linalg.norm(u_t)) < 1e-6
+    assert abs(ev_ - 100 * np.linalg.norm(v_t - vp) / np.linalg.norm(v_t)) < 1e-6
+    assert abs(ep - 100 * np.linalg.norm(p_t[m] - pp[m]) / np.linalg.norm(p_t[m])) < 1e-6
+    assert abs(eu - 100 * 0.01 / 1.01) < 1e-3
+    P.test(x, y, u_t, v_t, p_t, loop=7, save_dir=str(tmp_path))
+    d = scipy.io.loadmat(os.path.join(str(tmp_path), "cavity_result_loop_7.mat"))
+    for k in ("U_pred", "V_pred", "P_pred", "E_pred"):
+        assert d[k].shape == (385, 385)
+    assert {"error_u", "error_v", "error_p", "lam_bcs", "lam_equ"} <= set(d.keys())
+    assert np.allclose(d["U_pred"].reshape(-1), up.reshape(-1), rtol=0, atol=1e-6)
+
+
+def test_reference_checkpoint_files_and_full_state_resume(tmp_path):
+    import torch
+    from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+    from oracle.autograd_port import RefNet
+    P = _solver()
+    # weights-only files with the reference's directory scheme and state_dict keys (ev :742-759): they load into a plain
+    # module tree of the reference's shape, and back into a new solver through net_params / net_params_1 (ev :108-120)
+    out = P.save("model_cavity_loop0.pth", directory=str(tmp_path), N_HLayer=6, N_neu=80, N_f=2000)
+    assert out.endswith("/results/Re4000/6x80_Nf2k_lamB10_alpha0.03 /")
+    f0, f1 = out + "model_cavity_loop0.pth", out + "model_cavity_loop0.pth_evm"
+    ref = RefNet(2, 3, 6, 80)
+    ref.load_state_dict(torch.load(f0, map_location="cpu"))
+    assert np.array_equal(ref.flat(), P.net.flat_params().cpu().numpy())
+    Q = PysicsInformedNeuralNetwork(Re=4000, layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=2000, alpha_evm=0.03,
+                                    bc_weight=10, eq_weight=1, supervised_data_weight=0.0, net_params=f0, net_params_1=f1)
+    assert torch.equal(Q.net.flat_params(), P.net.flat_params()) and torch.equal(Q.net_1.flat_params(), P.net_1.flat_params())
+
+    # full state: 6 steps, checkpoint, 6 more  ==  load + 6 steps, bit for bit (both loops)
+    for fused in (False, True):
+        A = _solver(seed=5)
+        A.enable_fused_step(fused)
+        A.train(num_epoch=6, lr=1e-3)
+        ck = A.save_checkpoint(os.path.join(str(tmp_path), f"state_{int(fused)}.pt"))
+        lag = A.vis_t_minus.clone()
+
+        def more(S):      # continue WITHOUT re-creating the optimizer (solve_Adam's freeze at epoch 0 would, ev :452)
+            for _ in range(6):
+                if fused:
+                    S._fused_step_replayable()
+                else:
+                    loss, _ = S.fwd_computing_loss_2d(); S.opt.zero_grad(); loss.backward(); S.opt.step()
+        more(A)
+        B = _solver(seed=9)                      # different weights: everything must come from the file
+        B.enable_fused_step(fused)
+        B.load_checkpoint(ck)
+        assert torch.equal(B.vis_t_minus, lag) and B.global_step == 6
+        assert all(not p.requires_grad for p in B.net_1.parameters())
+        more(B)
+        assert torch.equal(A.net.flat_params(), B.net.flat_params()), fused
+        assert torch.equal(A.vis_t_minus, B.vis_t_minus)
