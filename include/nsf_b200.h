@@ -52,6 +52,9 @@ typedef struct {
 /* flags of NsfPhysics */
 #define NSF_HAS_EVM 1u       /* ev-NSFnet: second net, eq4, lagged entropy viscosity            */
 #define NSF_EVM_TRAINABLE 2u /* net_1 unfrozen (ev :501-511): also produce its gradient         */
+#define NSF_VTM_FROM_E 4u    /* nsf_step only: the lag state is initialised inside this call, vis_t_minus_in is ignored and
+                                vis_t = min(vis_t0, alpha_evm_init*|e|) with the e of THIS evaluation -- `init_vis_t()` (ev :138-140)
+                                followed by the first loss evaluation on unchanged net_1 weights, sharing one net_1 forward */
 
 /* Scalars of one loss evaluation -- ev-NSFnet/pinn_solver.py:32-54,67,311-342,387-397,426. */
 typedef struct {
@@ -61,8 +64,8 @@ typedef struct {
   float alpha_e;     /* eq_weight (ev :426)                                          */
   float coord_scale; /* 1.0 unless coordinate_transform (ev :311-324)                */
   float eq4_weight;  /* 0.1 (ev :397)                                                */
-  uint32_t flags;    /* NSF_HAS_EVM | NSF_EVM_TRAINABLE                              */
-  uint32_t reserved;
+  uint32_t flags;    /* NSF_HAS_EVM | NSF_EVM_TRAINABLE | NSF_VTM_FROM_E             */
+  float alpha_evm_init; /* alpha of `init_vis_t` (ev :140); read only with NSF_VTM_FROM_E */
   double n_f_norm;   /* denominator of the residual means; <=0 means n_f. Under data parallelism
                         pass the GLOBAL point count so that summing gradients over ranks gives
                         the gradient on the union of the shards. */

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libnsf_b200.so")
 NSF_OK = 0
 NSF_HAS_EVM = 1
 NSF_EVM_TRAINABLE = 2
+NSF_VTM_FROM_E = 4
 NSF_MAX_BLOCKS = 2
 NSF_LOSS_SLOTS = 16
 
@@ -31,7 +32,7 @@ class NsfNetDesc(C.Structure):
 
 class NsfPhysics(C.Structure):
     _fields_ = [("inv_Re", C.c_float), ("vis_t0", C.c_float), ("alpha_evm", C.c_float), ("alpha_e", C.c_float),
-                ("coord_scale", C.c_float), ("eq4_weight", C.c_float), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("coord_scale", C.c_float), ("eq4_weight", C.c_float), ("flags", C.c_uint32), ("alpha_evm_init", C.c_float),
                 ("n_f_norm", C.c_double)]
 
 
@@ -122,10 +123,12 @@ def check(lib: C.CDLL, rc: int) -> None:
 
 def physics(Re: float, *, vis_t0: Optional[float] = None, alpha_evm: float = 0.0, alpha_e: float = 1.0,
             coord_scale: float = 1.0, eq4_weight: float = 0.1, has_evm: bool = False, evm_trainable: bool = False,
-            n_f_norm: float = 0.0) -> NsfPhysics:
+            n_f_norm: float = 0.0, vtm_from_e_alpha: Optional[float] = None) -> NsfPhysics:
     flags = (NSF_HAS_EVM if has_evm else 0) | (NSF_EVM_TRAINABLE if (has_evm and evm_trainable) else 0)
+    if has_evm and vtm_from_e_alpha is not None:
+        flags |= NSF_VTM_FROM_E
     return NsfPhysics(1.0 / Re, (20.0 / Re) if vis_t0 is None else vis_t0, alpha_evm, alpha_e, coord_scale, eq4_weight,
-                      flags, 0, float(n_f_norm))
+                      flags, 0.0 if vtm_from_e_alpha is None else float(vtm_from_e_alpha), float(n_f_norm))
 
 
 class Context:

@@ -211,6 +211,27 @@ static int wall_run(const float* x, const float* y, long long n, const float* xb
 }
 #endif
 
+// out[i] = scale * |in[i]|: the lag state of `init_vis_t` (ev :138-140) from the net_1 output this step computed anyway
+#ifndef NSF_EMU
+namespace {
+__global__ void nsf_scale_abs_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = scale * fabsf(in[i]);
+}
+}  // namespace
+int nsf_scale_abs_launch(const float* in, float* out, long long n, float scale, nsf_stream_t st) {
+  if (n <= 0) return NSF_OK;
+  nsf_scale_abs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, scale);
+  NSF_CUDA_OK(cudaGetLastError());
+  return NSF_OK;
+}
+#else
+int nsf_scale_abs_launch(const float* in, float* out, long long n, float scale, nsf_stream_t) {
+  for (long long i = 0; i < n; ++i) out[i] = scale * std::fabs(in[i]);
+  return NSF_OK;
+}
+#endif
+
 static int ok_ptr(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 extern "C" int nsf_adam_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, NsfAdamDev* state,

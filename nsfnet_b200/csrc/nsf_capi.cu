@@ -442,6 +442,11 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
       float* eb = e_out ? e_out : ctx->e_buf;
       NSF_TRY(evm_forward(ctx, params_evm, evm_train, x, y, n_f, eb, st));
       e_ptr = eb;
+      if (ph->flags & NSF_VTM_FROM_E) {   // init_vis_t fused into this evaluation: the lag state it would have left behind
+        if (!valid_ptr(vtm_out)) { nsf_set_error("nsf_step: NSF_VTM_FROM_E needs vis_t_minus_out"); return NSF_E_ARG; }
+        NSF_TRY(nsf_scale_abs_launch(eb, vtm_out, n_f, ph->alpha_evm_init, st)); ctx->launches++;
+        vtm_in = vtm_out;
+      }
     }
     NsfKernelArgs a;
     base_args(a, M, x, y, n_f, NSF_MODE_JET_STEP);

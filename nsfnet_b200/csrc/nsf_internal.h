@@ -85,6 +85,9 @@ int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, con
 int nsf_adam_launch(float* params, const float* grad, float* m, float* v, long long n, float lr, float b1, float b2,
                     float eps, float bc1, float bc2, float grad_scale, nsf_stream_t st);
 
+// nsf_aux.cu: out = scale * |in|
+int nsf_scale_abs_launch(const float* in, float* out, long long n, float scale, nsf_stream_t st);
+
 // nsf_value_fwd.cu (CUDA build only): one-output value forward, thread per point ----------------------------------
 int nsf_value_fwd_supported(const NsfNetGeom& g);
 int nsf_value_fwd_launch(const NsfNetGeom& g, int sms, const float* flat, const float* x, const float* y, long long n, float* out,

@@ -76,6 +76,23 @@ class SolverBase:
     global_step = 0
     HAS_EVM = False
     verbose = True
+    # `init_vis_t` (ev :138-140, called by set_eq_training_data :184) is deferred into the first loss evaluation on the new
+    # points, which computes the same net_1 forward anyway (NSF_VTM_FROM_E): identical lag state, one forward instead of two.
+    # Any read of `vis_t_minus` before that evaluates it on the spot; set to False to always evaluate it in the setter.
+    lazy_init_vis_t = True
+    _vtm = None
+    _vtm_pending = None
+
+    @property
+    def vis_t_minus(self):
+        if self._vtm_pending is not None:
+            self._materialise_vis_t()
+        return self._vtm
+
+    @vis_t_minus.setter
+    def vis_t_minus(self, value):
+        self._vtm = value
+        self._vtm_pending = None
 
     # ------------------------------------------------------------------------------------
     def _init_common(self, Re, layers, hidden_size, N_f, bc_weight, eq_weight, num_ins, num_outs, learning_rate,
@@ -264,24 +281,42 @@ class SolverBase:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _phys(self, n_f_norm=0.0):
+    def _phys(self, n_f_norm=0.0, vtm_from_e_alpha=None):
         trainable = self.HAS_EVM and any(p.requires_grad for p in self.net_1.parameters())
         return _capi.physics(float(self.Re), vis_t0=(20.0 / self.Re) if self.HAS_EVM else 0.0, alpha_evm=float(self.alpha_evm),
                              alpha_e=float(self.alpha_e), coord_scale=float(self.coord_scale), eq4_weight=0.1,
-                             has_evm=self.HAS_EVM, evm_trainable=trainable, n_f_norm=float(n_f_norm))
+                             has_evm=self.HAS_EVM, evm_trainable=trainable, n_f_norm=float(n_f_norm),
+                             vtm_from_e_alpha=vtm_from_e_alpha)
 
-    def _forward_net(self, which, x, y):
+    def _forward_net(self, which, x, y, params=None):
         net = self.net if which == 0 else self.net_1
         x = _dev_f32(x, self.device); y = _dev_f32(y, self.device)
         n = x.numel()
         out = torch.empty((n, net.num_outs), dtype=torch.float32, device=self.device)
-        self._ctx.forward(which, net.flat_params().data_ptr(), x.data_ptr(), y.data_ptr(), n, out.data_ptr(), self._stream())
+        flat = net.flat_params() if params is None else params
+        self._ctx.forward(which, flat.data_ptr(), x.data_ptr(), y.data_ptr(), n, out.data_ptr(), self._stream())
         return out
+
+    def _evm_version(self):
+        """Changes whenever net_1's weights are written through the module (optimizer step, load_state_dict, copy_) or
+        through the flat buffer."""
+        return (self.net_1.flat_params()._version,) + tuple(p._version for p in self.net_1.parameters())
 
     def init_vis_t(self):
         """vis_t_minus = alpha_evm * |e(x_f, y_f)| with the current weights (ev :138-140)."""
-        e = self._forward_net(1, self.x_f, self.y_f)
-        self.vis_t_minus = (float(self.alpha_evm) * e.abs()).reshape(-1).contiguous()
+        if not self.lazy_init_vis_t:
+            e = self._forward_net(1, self.x_f, self.y_f)
+            self.vis_t_minus = (float(self.alpha_evm) * e.abs()).reshape(-1).contiguous()
+            return
+        self._vtm = None
+        self._vtm_pending = dict(alpha=float(self.alpha_evm), version=self._evm_version(), n=self.x_f.numel(),
+                                 snapshot=self.net_1.flat_params().detach().clone(), x=self.x_f, y=self.y_f)
+
+    def _materialise_vis_t(self):
+        p, self._vtm_pending = self._vtm_pending, None
+        params = None if self._evm_version() == p["version"] else p["snapshot"]     # the weights of the time of the call
+        e = self._forward_net(1, p["x"], p["y"], params=params)
+        self._vtm = (p["alpha"] * e.abs()).reshape(-1).contiguous()
 
     def _launch_step(self):
         net, net1 = self.net, self.net_1
@@ -306,16 +341,25 @@ class SolverBase:
                                              self.p_s.data_ptr() if self.p_s is not None else None,
                                              self.supervision_point_count, cs, cs, cp, 0))
         w = self.eq_weights if (self.eq_weights is not None and self.eq_weights.numel() == n_f) else None
-        vtm = self.vis_t_minus if (self.HAS_EVM and self.vis_t_minus is not None and self.vis_t_minus.numel() == n_f) else None
-        if self.HAS_EVM and vtm is None:
+        lazy_alpha = None
+        pend = self._vtm_pending
+        if self.HAS_EVM and pend is not None:
+            if pend["n"] == n_f and pend["x"] is self.x_f and self._evm_version() == pend["version"]:
+                lazy_alpha = pend["alpha"]          # init_vis_t fused into this evaluation (same weights, same points)
+                self._vtm_pending = None
+                self._vtm = torch.empty(n_f, dtype=torch.float32, device=self.device)
+            else:
+                self._materialise_vis_t()
+        vtm = self._vtm if (self.HAS_EVM and lazy_alpha is None and self._vtm is not None and self._vtm.numel() == n_f) else None
+        if self.HAS_EVM and vtm is None and lazy_alpha is None:
             self.vis_t_minus = torch.empty(n_f, dtype=torch.float32, device=self.device)
-        phys = self._phys(n_f_glob)
+        phys = self._phys(n_f_glob, vtm_from_e_alpha=lazy_alpha)
         gm = self._buf
         ge = self._buf[self._n_main:] if self._n_evm else None
         keep = self.store_residuals
         self._ctx.step(pm.data_ptr(), pe.data_ptr() if pe is not None else None, self.x_f.data_ptr(), self.y_f.data_ptr(),
                        w.data_ptr() if w is not None else None, vtm.data_ptr() if vtm is not None else None,
-                       self.vis_t_minus.data_ptr() if self.HAS_EVM else None, n_f, blocks, phys,
+                       self._vtm.data_ptr() if self.HAS_EVM else None, n_f, blocks, phys,
                        gm.data_ptr(), ge.data_ptr() if ge is not None else None, self._parts.data_ptr(),
                        self._resid.data_ptr() if keep else None, self._e.data_ptr() if self.HAS_EVM else None,
                        self._vis.data_ptr() if self.HAS_EVM else None, self._stream())
@@ -455,7 +499,7 @@ class SolverBase:
     def _graph_key(self):
         ptr = lambda t: 0 if t is None else t.data_ptr()
         trainable = self.HAS_EVM and any(p.requires_grad for p in self.net_1.parameters())
-        return (ptr(self.x_f), ptr(self.y_f), self.x_f.numel(), ptr(self.eq_weights), ptr(self.x_b), ptr(self.vis_t_minus),
+        return (ptr(self.x_f), ptr(self.y_f), self.x_f.numel(), ptr(self.eq_weights), ptr(self.x_b), ptr(self._vtm), self._vtm_pending is None,
                 ptr(self.x_s), ptr(self.p_s), self.supervision_enabled, float(self.alpha_evm), float(self.alpha_b), float(self.alpha_e),
                 float(self.alpha_s), float(self.coord_scale), trainable, self.store_residuals, self._n_f_global,
                 ptr(self.net.flat_params()), ptr(self.net_1.flat_params()) if self.net_1 is not None else 0)

@@ -92,3 +92,27 @@ def test_wall_distance_and_sdf_weights_match_ckdtree(lib):
     # the reference's clamps (cavity_data.py:123-126)
     _capi.check(lib, lib.nsf_sdf_weights(P(x), P(y), n, P(xb32), P(yb32), xb32.size, 7.0, -3.0, P(w), None, None))
     assert np.allclose(w, 1.0)
+
+
+def test_vtm_from_e_equals_explicit_init(lib):
+    """NSF_VTM_FROM_E: `init_vis_t` (ev :138-140) fused into the first loss evaluation == passing alpha_init*|e| explicitly."""
+    from oracle import jet_numpy as J
+    rng = np.random.default_rng(3)
+    md, ed = J.NetDesc(2, 3, 3, 16), J.NetDesc(2, 1, 4, 40)
+    pm, pe = J.init_params(md, 1) * 1.5, J.init_params(ed, 2) * 3.0
+    n, nb = 70, 9
+    x, y = rng.random(n), rng.random(n)
+    xb, yb, ub, vb = rng.random(nb), rng.random(nb), rng.random(nb), rng.random(nb)
+    blocks = [(xb, yb, ub, vb, None, 10. / nb, 10. / nb, 0.)]
+    a_init, a_now = 0.05, 0.03
+    base = emu.run_step(lib, (2, 3, 3, 16), pm, _capi.physics(50., alpha_evm=a_now, has_evm=True), x, y, blocks=blocks,
+                        evm_desc=(2, 1, 4, 40), params_evm=pe)                     # gives e
+    vtm0 = (np.float32(a_init) * np.abs(base["e"])).astype(np.float32)
+    assert (vtm0 < 20. / 50.).any()                                             # the cap is not active everywhere
+    want = emu.run_step(lib, (2, 3, 3, 16), pm, _capi.physics(50., alpha_evm=a_now, has_evm=True), x, y, blocks=blocks,
+                        evm_desc=(2, 1, 4, 40), params_evm=pe, vtm_in=vtm0)
+    got = emu.run_step(lib, (2, 3, 3, 16), pm, _capi.physics(50., alpha_evm=a_now, has_evm=True, vtm_from_e_alpha=a_init), x, y,
+                       blocks=blocks, evm_desc=(2, 1, 4, 40), params_evm=pe)
+    for k in ("grad_main", "loss_parts", "resid", "vis_t", "vtm_out", "e"):
+        assert np.array_equal(got[k], want[k]), k
+    assert not np.array_equal(got["vis_t"], base["vis_t"])

@@ -146,3 +146,37 @@ def test_device_point_layer_matches_host_layer():
     assert P.x_f.data_ptr() == xd.data_ptr() and P._n_f_global == 50_000
     loss, _ = P.fwd_computing_loss_2d()
     assert np.isfinite(float(loss))
+
+
+def test_deferred_init_vis_t_equals_the_setter_time_forward():
+    """`init_vis_t` (ev :138-140) is fused into the first loss evaluation on new points (NSF_VTM_FROM_E); reading
+    `vis_t_minus` earlier, or changing net_1 in between, must give exactly what the reference's eager call gives."""
+    import torch
+
+    def run(mode):
+        P = _ev(seed=4)
+        with torch.no_grad():
+            P.net_1.flat_params().mul_(4.0)           # |e| large enough that min(vis_t0, alpha |e|) is not the cap everywhere
+        P.set_eq_training_data((P.x_f.cpu().numpy(), P.y_f.cpu().numpy()))      # (re)initialises the lag state with alpha = 0.05
+        if mode == "eager":
+            assert P._vtm_pending is not None
+            _ = P.vis_t_minus                          # evaluated on the spot
+            assert P._vtm_pending is None
+        if mode in ("changed", "changed_eager"):
+            if mode == "changed_eager":
+                _ = P.vis_t_minus
+            with torch.no_grad():
+                P.net_1.layers.layer_0.weight.mul_(1.25)     # through the module: the deferred forward must use the old weights
+        P.set_alpha_evm(0.03)
+        P.freeze_evm_net(0)
+        loss, _ = P.fwd_computing_loss_2d(); P.opt.zero_grad(); loss.backward()
+        g = torch.cat([p.grad.reshape(-1) for p in P.net.parameters()]).clone()
+        return float(loss), g, P.vis_t.clone(), P.vis_t_minus.clone()
+    le, ge, ve, me = run("eager")
+    ll, gl, vl, ml = run("lazy")
+    assert ll == le and torch.equal(gl, ge) and torch.equal(vl, ve) and torch.equal(ml, me)
+    assert (ve < 20.0 / 2000.0).float().mean().item() > 0.005      # the cap is not active everywhere
+    lc, gc, vc, mc = run("changed")
+    lce, gce, vce, mce = run("changed_eager")
+    assert lc == lce and torch.equal(gc, gce) and torch.equal(vc, vce) and torch.equal(mc, mce)
+    assert torch.equal(vc, ve) and not torch.equal(mc, me)     # vis_t from the OLD weights' e, the new lag state from the new ones
