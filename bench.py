@@ -261,19 +261,21 @@ def main():
     adam_steps_s = time_iters(P._fused_step_replayable, args.steps)
     P.enable_fused_step(False)
     small = None
-    if world == 1 and not args.no_small:
+    if not args.no_small:
         # the shipped configuration's point count (ev-NSFnet/configs/production.yaml: N_f = 120 000), where the iteration is
         # launch / Python bound rather than kernel bound
         n_s = 120_000
         x_s = torch.rand(n_s, device=dev, generator=g); y_s = torch.rand(n_s, device=dev, generator=g)
-        P.set_eq_training_shard((x_s, y_s), n_global=n_s)
+        P.set_eq_training_shard((x_s, y_s), n_global=n_s * world)
         if args.workload == "ev":
             P.freeze_evm_net(0)
         a = time_iters(adam_iter, 200)
         fused_on(P)
         b = time_iters(P._fused_step_replayable, 200)
         P.enable_fused_step(False)
-        small = {"n_f": n_s, "adam_steps_per_s_torch_optim_loop": a, "adam_steps_per_s_fused_graph": b}
+        graphed = world == 1 or os.environ.get("NSF_FUSED_GRAPH_DDP", "1") == "1"
+        small = {"n_f_per_gpu": n_s, "adam_steps_per_s_torch_optim_loop": a,
+                 "adam_steps_per_s_fused_graph" if graphed else "adam_steps_per_s_fused_eager": b}
         P.set_eq_training_shard((x, y), n_global=n * world)
         if args.workload == "ev":
             P.freeze_evm_net(0)
@@ -322,7 +324,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "adam_steps_per_s": adam_steps_s, "adam_steps_per_s_torch_optim_loop": adam_torch_steps_s,
             "adam_iteration": "nsf_step + device-resident Adam (nsf_adam_dev), one CUDA graph replay per iteration" if world == 1
-                              else "nsf_step + NCCL all-reduce + device-resident Adam (nsf_adam_dev), launched eagerly",
+                              else ("nsf_step + NCCL all-reduce + device-resident Adam (nsf_adam_dev), " +
+                                    ("one CUDA graph replay per iteration" if os.environ.get("NSF_FUSED_GRAPH_DDP", "1") == "1" else "launched eagerly")),
             "adam_small_batch": small,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get((args.workload, info["path"], n)),

@@ -463,6 +463,14 @@ class SolverBase:
         self._fused, self._fused_graph = bool(enabled), bool(graph)
         self._graphs = {}
 
+    def release_graphs(self):
+        """Drop the captured iterations.  Under data parallelism call this before ``dist.destroy_process_group()``: a live
+        CUDA graph that holds NCCL kernels makes the communicator teardown wait forever."""
+        import gc
+        self._graphs = {}
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+
     def _adam_reset(self):
         """A new ``torch.optim.Adam``: zero moments, step 0 (betas (0.9, 0.999), eps 1e-8, ev :126-129)."""
         n = self._n_main + self._n_evm
@@ -507,7 +515,9 @@ class SolverBase:
     def _fused_step_replayable(self):
         """Iteration through a captured graph when allowed (single process, timing hooks off), else eagerly.  The first call for
         a configuration runs eagerly (it creates the library's workspaces) and captures afterwards."""
-        use_graph = self._fused_graph and not self.is_distributed
+        # under data parallelism the NCCL all-reduce sits in the middle of the iteration and is captured with it (NCCL >= 2.9.6;
+        # the collective has run eagerly in the warm-up iteration); NSF_FUSED_GRAPH_DDP=0 launches the iteration eagerly instead
+        use_graph = self._fused_graph and (not self.is_distributed or os.environ.get("NSF_FUSED_GRAPH_DDP", "1") == "1")
         if not use_graph:
             return self._fused_iteration()
         key = self._graph_key()

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .cavity_data import DataLoader
+from .cavity_data import DataLoader, DeviceDataLoader
 from .config import ConfigManager
 
 
@@ -26,6 +26,10 @@ def parse_args(argv=None):
     p.add_argument("--dry-run", action="store_true")
     p.add_argument("--eval-file", type=str, default=None, help="DNS .mat (X_ref,Y_ref,U_ref,V_ref,P_ref); default ./data/cavity_Re{Re}_256_Uniform.mat")
     p.add_argument("--seed", type=int, default=None)
+    p.add_argument("--no-fused", action="store_true", help="keep the reference's per-iteration Python (loss.backward() + torch.optim.Adam) "
+                   "instead of the fused iteration (nsf_step + device-resident Adam replayed as one CUDA graph)")
+    p.add_argument("--device-data", action="store_true", help="generate the collocation set (Latin hypercube, wall-distance sort, SDF "
+                   "weights) on the GPU, every rank its own rows, instead of the host data layer")
     return p.parse_args(argv)
 
 
@@ -67,18 +71,23 @@ def main(argv=None):
     try:
         PINN = build_pinn(cfg)
         PINN.log_interval = cfg.training.log_interval
+        PINN.enable_fused_step(not args.no_fused)
         if rank == 0 and cfg.training.enable_tensorboard:
             try:
                 from torch.utils.tensorboard import SummaryWriter
                 PINN.tb_writer = SummaryWriter(log_dir=os.path.join(cfg.training.tb_log_dir, f"{cfg.experiment_name}_{time.strftime('%Y%m%d_%H%M%S')}"))
             except Exception as e:      # tensorboard is optional
                 print(f"TensorBoard disabled: {e}")
-        loader = DataLoader(N_f=cfg.training.N_f, N_b=1000, sort_training_points=cfg.training.sort_training_points,
-                            sdf_weighting=cfg.training.sdf_weighting, coord_transform=cfg.training.coordinate_transform, seed=args.seed)
+        kw = dict(N_f=cfg.training.N_f, N_b=1000, sort_training_points=cfg.training.sort_training_points,
+                  sdf_weighting=cfg.training.sdf_weighting, coord_transform=cfg.training.coordinate_transform, seed=args.seed)
+        loader = DeviceDataLoader(PINN.device, rank=PINN.rank, world_size=PINN.world_size, **kw) if args.device_data else DataLoader(**kw)
         PINN.set_boundary_data(X=loader.loading_boundary_data())
         train_pts = loader.loading_training_data()
         PINN.set_coordinate_transform(loader.get_coord_scale())
-        PINN.set_eq_training_data(X=train_pts, weights=loader.get_sdf_weights())
+        if args.device_data:
+            PINN.set_eq_training_shard(train_pts, weights=loader.get_sdf_weights(), n_global=cfg.training.N_f)
+        else:
+            PINN.set_eq_training_data(X=train_pts, weights=loader.get_sdf_weights())
         eval_file = args.eval_file or f"./data/cavity_Re{cfg.physics.Re}_256_Uniform.mat"
         eval_data = loader.loading_evaluate_data(eval_file) if os.path.exists(eval_file) else None
         sup = cfg.supervision
@@ -107,6 +116,8 @@ def main(argv=None):
         if PINN.tb_writer is not None:
             PINN.tb_writer.close()
     finally:
+        if "PINN" in locals():
+            PINN.release_graphs()
         if distributed and dist.is_initialized():
             dist.destroy_process_group()
     return 0
