@@ -108,6 +108,7 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
 #ifndef NSF_EMU
   nsf_umma_free(ctx);
   nsf_umma2_free(ctx);
+  nsf_umma3_free(ctx);
   if (ctx->side) cudaStreamDestroy((cudaStream_t)ctx->side);
   if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
@@ -125,12 +126,13 @@ static int effective_path(const NsfCtx* ctx) {
 #else
   if (ctx->path == 1) return 1;
   if (!nsf_umma_supported(ctx->main.g)) return 1;
+  if (ctx->path == 4) return 4;
   return ctx->path == 3 ? 3 : 2;
 #endif
 }
 
 extern "C" int nsf_set_path(NsfCtx* ctx, int path) {
-  if (!ctx || path < 0 || path > 3) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
+  if (!ctx || path < 0 || path > 4) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
 #ifdef NSF_EMU
   if (path >= 2) { nsf_set_error("tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE; }
 #else
@@ -161,6 +163,7 @@ extern "C" int nsf_get_stage_cycles(NsfCtx* ctx, double* out) {
   (void)out; nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE;
 #else
   if (!nsf_umma_supported(ctx->main.g)) { nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not cover this net"); return NSF_E_SHAPE; }
+  if (effective_path(ctx) == 4) return nsf_umma3_stage_cycles(ctx, out);
   return effective_path(ctx) == 3 ? nsf_umma2_stage_cycles(ctx, out) : nsf_umma_stage_cycles(ctx, out);
 #endif
 }
@@ -175,6 +178,10 @@ static int launch_jet(NsfCtx* ctx, NsfKernelArgs& a, const float* flat_main, int
   if (effective_path(ctx) == 3) {
     NSF_TRY(nsf_umma2_init(ctx));
     return nsf_umma2_launch(ctx, a, flat_main, grid, st, &ctx->launches);
+  }
+  if (effective_path(ctx) == 4) {
+    NSF_TRY(nsf_umma3_init(ctx));
+    return nsf_umma3_launch(ctx, a, flat_main, grid, st, &ctx->launches);
   }
 #endif
   (void)flat_main;
@@ -350,6 +357,11 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   int grids[1 + NSF_MAX_BLOCKS];
   grids[0] = n_f > 0 ? grid_for(ctx, M, 4, n_f) : 0;
 #ifndef NSF_EMU
+  if (n_f > 0 && effective_path(ctx) == 4) {
+    NSF_TRY(nsf_umma3_init(ctx));
+    const long long groups = (n_f + nsf_umma3_group_points() - 1) / nsf_umma3_group_points();
+    grids[0] = (int)(groups < ctx->sms ? groups : ctx->sms);
+  }
   if (n_f > 0 && effective_path(ctx) == 2) {   // one persistent CTA per SM, a pair of 8-point tiles per iteration
     NSF_TRY(nsf_umma_init(ctx));
     const long long groups = (n_f + nsf_umma_group_points() - 1) / nsf_umma_group_points();
@@ -371,7 +383,7 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   }
   bool side = false;
 #ifndef NSF_EMU
-  side = n_f > 0 && effective_path(ctx) == 2 && blk_rows > 0 && grids[0] + blk_rows <= M.rows;
+  side = n_f > 0 && (effective_path(ctx) == 2 || effective_path(ctx) == 4) && blk_rows > 0 && grids[0] + blk_rows <= M.rows;
   if (side && !ctx->side) {
     cudaStream_t s2; cudaEvent_t e0, e1;
     NSF_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));

@@ -62,6 +62,7 @@ struct NsfCtx {
   long long cap = 0;
   void* umma = nullptr;  // tcgen05 path state, tile-major kernel (nsf_umma_jet.cu)
   void* umma2 = nullptr; // tcgen05 path state, layer-major kernel (nsf_umma_jet2.cu)
+  void* umma3 = nullptr; // tcgen05 path state, tile-major kernel with the weights in tensor memory (nsf_umma_jet3.cu)
   int umma2_nt = 0;      // tiles per super-batch of the layer-major kernel (0 = default)
   void* side = nullptr;     // side stream: the data blocks (boundary / supervised MSE) run beside the EVM forward + jet kernel
   void* ev_fork = nullptr;
@@ -104,6 +105,11 @@ void nsf_umma2_free(NsfCtx* ctx);
 int nsf_umma2_stage_cycles(NsfCtx* ctx, double* out);
 int nsf_umma2_grid(const NsfCtx* ctx, long long n, int nt);
 int nsf_umma2_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
+int nsf_umma3_group_points();
+int nsf_umma3_init(NsfCtx* ctx);
+void nsf_umma3_free(NsfCtx* ctx);
+int nsf_umma3_stage_cycles(NsfCtx* ctx, double* out);
+int nsf_umma3_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 
 // flat parameter i of the packed image (host + device)

@@ -197,7 +197,7 @@ def test_full_size_properties(gu):
 # ---- tcgen05 (3xTF32) path: same bar as the FP32 path -------------------------------------------------
 @pytest.mark.parametrize("L,n,nb", [(6, 1333, 132), (2, 16, 8), (3, 5, 3), (6, 100000, 2052), (4, 777, 40)])
 @pytest.mark.parametrize("has_evm", [False, True])
-@pytest.mark.parametrize("path", [2, 3])
+@pytest.mark.parametrize("path", [2, 3, 4])
 def test_umma_step_matches_oracle(gu, L, n, nb, has_evm, path):
     H = 80
     rng = np.random.default_rng(L * 100 + n)
@@ -233,7 +233,7 @@ def test_umma_step_matches_oracle(gu, L, n, nb, has_evm, path):
     assert np.array_equal(o["grad_main"], o2["grad_main"])
 
 
-@pytest.mark.parametrize("path", [2, 3])
+@pytest.mark.parametrize("path", [2, 3, 4])
 def test_umma_golden_ev_lag(gu, golden_dir, path):
     g = np.load(os.path.join(golden_dir, "ev_re2000_lag.npz"))
     xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
