@@ -105,13 +105,14 @@ const char* nsf_last_error(void);
 int nsf_create(int device, const NsfNetDesc* main_net, const NsfNetDesc* evm_or_null, NsfCtx** out);
 int nsf_destroy(NsfCtx* ctx);
 
-/* Select the kernel family of the hidden-layer contractions: 0 = auto (tcgen05 when the shape is
- * covered, else FFMA), 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 tile-major kernel (default for hidden = 80), 3 = tcgen05
- * 3xTF32 layer-major kernel (weights in tensor memory); 2 / 3 return NSF_E_SHAPE if the shape is not covered. */
+/* Select the kernel family of the hidden-layer contractions: 0 = auto (tcgen05 tile-major when the shape is covered, else
+ * FFMA), 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 tile-major kernel (default for hidden = 80), 3 = tcgen05 3xTF32
+ * layer-major kernel (weights in tensor memory, per-tile state through L2), 4 = tcgen05 3xTF32 tile-major kernel with the
+ * stage weights in tensor memory (experimental); 2 / 3 / 4 return NSF_E_SHAPE if the shape is not covered. */
 int nsf_set_path(NsfCtx* ctx, int path);
 /* Tuning knob of the layer-major kernel: 12-point tiles per super-batch (1..8, 0 = default 4). */
 int nsf_set_tiles_per_batch(NsfCtx* ctx, int nt);
-/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 2, 3 tcgen05),
+/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 2, 3, 4 tcgen05),
  * [2]=kernel launches issued by the last nsf_* call, [3]=workspace bytes. */
 int nsf_get_info(NsfCtx* ctx, int64_t info[4]);
 
