@@ -8,14 +8,16 @@
 //   * the thread's activations of the previous layer are registers (k loop unrolled), the new ones go to a
 //     per-thread column of shared memory (act[j][tid]: consecutive threads -> consecutive banks) because the output
 //     neuron index j is a run-time loop variable;
-//   * no barrier after the parameter load: threads only touch their own column.
+//   * no barrier after the parameter load: threads only touch their own columns;
+//   * a thread carries TWO points (i, i + 128), so every weight fetch is used twice and eight accumulation chains are in flight.
 // Template on the hidden width (40: production.yaml / config.py; 20: the reference ctor default hidden_size_1).
 #include "nsf_internal.h"
 #include "nsf_math.cuh"
 
 namespace {
 
-constexpr int VT = 128;   // threads (points) per CTA pass
+constexpr int VT = 128;   // threads per CTA
+constexpr int NP = 2;     // points per thread and pass
 
 template <int H>
 __global__ void __launch_bounds__(VT) nsf_value_fwd_kernel(int L, const float* __restrict__ flat, const float* __restrict__ x,
@@ -27,7 +29,7 @@ __global__ void __launch_bounds__(VT) nsf_value_fwd_kernel(int L, const float* _
   constexpr int PER = H * H + H;
   float* wl = hid + (L - 1) * PER;
   const int psz = 3 * H + (L - 1) * PER + H + 4;
-  float* act = vsm + ((psz + 3) & ~3);          // [H][VT]
+  float* act = vsm + ((psz + 3) & ~3);          // [H][NP * VT]
   const int tid = threadIdx.x;
 
   // flat (state_dict) order: W0[H][2], b0[H], (W_l[H j][H k], b_l[H]) l = 1..L-1, WL[1][H], bL[1]
@@ -45,50 +47,76 @@ __global__ void __launch_bounds__(VT) nsf_value_fwd_kernel(int L, const float* _
   }
   __syncthreads();
 
+  // two points per thread (i and i + VT): one broadcast LDS.128 of W[j..j+3][k] feeds 8 FFMA on 8 independent chains
   float* col = act + tid;
-  for (long long base = (long long)blockIdx.x * VT; base < n; base += (long long)gridDim.x * VT) {
-    const long long i = base + tid;
-    const bool ok = i < n;
-    const float xv = ok ? __ldg(x + i) : 0.f, yv = ok ? __ldg(y + i) : 0.f;
-#pragma unroll 4
+  constexpr int RS = NP * VT;                    // row stride of the activation columns
+  for (long long base = (long long)blockIdx.x * RS; base < n; base += (long long)gridDim.x * RS) {
+    float xv[NP], yv[NP];
+    bool ok[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const long long i = base + q * VT + tid;
+      ok[q] = i < n;
+      xv[q] = ok[q] ? __ldg(x + i) : 0.f;
+      yv[q] = ok[q] ? __ldg(y + i) : 0.f;
+    }
+#pragma unroll 2
     for (int j = 0; j < H; j += 4) {
       const float4 wx = *reinterpret_cast<const float4*>(w0x + j), wy = *reinterpret_cast<const float4*>(w0y + j),
                    bb = *reinterpret_cast<const float4*>(b0 + j);
-      col[(j + 0) * VT] = nsf_tanh_fast(fmaf(wx.x, xv, fmaf(wy.x, yv, bb.x)));
-      col[(j + 1) * VT] = nsf_tanh_fast(fmaf(wx.y, xv, fmaf(wy.y, yv, bb.y)));
-      col[(j + 2) * VT] = nsf_tanh_fast(fmaf(wx.z, xv, fmaf(wy.z, yv, bb.z)));
-      col[(j + 3) * VT] = nsf_tanh_fast(fmaf(wx.w, xv, fmaf(wy.w, yv, bb.w)));
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        col[(j + 0) * RS + q * VT] = nsf_tanh_fast(fmaf(wx.x, xv[q], fmaf(wy.x, yv[q], bb.x)));
+        col[(j + 1) * RS + q * VT] = nsf_tanh_fast(fmaf(wx.y, xv[q], fmaf(wy.y, yv[q], bb.y)));
+        col[(j + 2) * RS + q * VT] = nsf_tanh_fast(fmaf(wx.z, xv[q], fmaf(wy.z, yv[q], bb.z)));
+        col[(j + 3) * RS + q * VT] = nsf_tanh_fast(fmaf(wx.w, xv[q], fmaf(wy.w, yv[q], bb.w)));
+      }
     }
     for (int l = 1; l < L; ++l) {
-      float a[H];
+      float a[NP][H];
 #pragma unroll
-      for (int k = 0; k < H; ++k) a[k] = col[k * VT];
+      for (int k = 0; k < H; ++k)
+#pragma unroll
+        for (int q = 0; q < NP; ++q) a[q][k] = col[k * RS + q * VT];
       const float* Wt = hid + (l - 1) * PER;
 #pragma unroll 1
       for (int j = 0; j < H; j += 4) {
-        float4 z = *reinterpret_cast<const float4*>(Wt + H * H + j);
+        const float4 bz = *reinterpret_cast<const float4*>(Wt + H * H + j);
+        float4 z[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) z[q] = bz;
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           const float4 w = *reinterpret_cast<const float4*>(Wt + k * H + j);
-          z.x = fmaf(w.x, a[k], z.x); z.y = fmaf(w.y, a[k], z.y); z.z = fmaf(w.z, a[k], z.z); z.w = fmaf(w.w, a[k], z.w);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            z[q].x = fmaf(w.x, a[q][k], z[q].x); z[q].y = fmaf(w.y, a[q][k], z[q].y);
+            z[q].z = fmaf(w.z, a[q][k], z[q].z); z[q].w = fmaf(w.w, a[q][k], z[q].w);
+          }
         }
-        col[(j + 0) * VT] = nsf_tanh_fast(z.x);
-        col[(j + 1) * VT] = nsf_tanh_fast(z.y);
-        col[(j + 2) * VT] = nsf_tanh_fast(z.z);
-        col[(j + 3) * VT] = nsf_tanh_fast(z.w);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          col[(j + 0) * RS + q * VT] = nsf_tanh_fast(z[q].x);
+          col[(j + 1) * RS + q * VT] = nsf_tanh_fast(z[q].y);
+          col[(j + 2) * RS + q * VT] = nsf_tanh_fast(z[q].z);
+          col[(j + 3) * RS + q * VT] = nsf_tanh_fast(z[q].w);
+        }
       }
     }
-    float o = wl[H];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      float o = wl[H];
 #pragma unroll 8
-    for (int k = 0; k < H; ++k) o = fmaf(wl[k], col[k * VT], o);
-    if (ok) out[i] = o;
+      for (int k = 0; k < H; ++k) o = fmaf(wl[k], col[k * RS + q * VT], o);
+      if (ok[q]) out[base + q * VT + tid] = o;
+    }
   }
 }
 
 template <int H>
 size_t value_fwd_smem(int L) {
   const int psz = 3 * H + (L - 1) * (H * H + H) + H + 4;
-  return sizeof(float) * (size_t)(((psz + 3) & ~3) + H * VT);
+  return sizeof(float) * (size_t)(((psz + 3) & ~3) + H * VT * NP);
 }
 
 }  // namespace
@@ -108,7 +136,7 @@ int nsf_value_fwd_launch(const NsfNetGeom& g, int sms, const float* flat, const 
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
-  long long blocks = (n + VT - 1) / VT;
+  long long blocks = (n + VT * NP - 1) / (VT * NP);
   const long long cap = (long long)sms * per_sm;
   if (blocks > cap) blocks = cap;
   if (g.H == 40) {

@@ -140,3 +140,34 @@ def test_ev_curve_tracks_reference(golden_dir):
     P.solve_Adam(rec, int(g["steps"]))
     c = np.array(curve[::int(g["every"])])
     assert_tracks(c, g, "curve_ev_re2000")
+
+
+def test_lbfgs_closure_works_on_the_drop_in_solver():
+    """The optimizer stays PyTorch's (BASELINE north star: "the Adam/L-BFGS update stays in PyTorch"): `loss.backward()`
+    on the tensor returned by fwd_computing_loss_2d fills p.grad, so a torch.optim.LBFGS closure drives the CUDA path
+    unchanged.  Every closure call also advances the lagged viscosity, exactly as it would with the reference."""
+    import torch
+    from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+    torch.manual_seed(2)
+    P = PysicsInformedNeuralNetwork(Re=2000, layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=4000, alpha_evm=0.05,
+                                    bc_weight=10, eq_weight=1, supervised_data_weight=0.0)
+    rng = np.random.default_rng(0)
+    xb, yb, ub, vb = J.cavity_boundary(129)
+    P.set_boundary_data((xb, yb, ub, vb))
+    P.set_eq_training_data((rng.random(4000).astype(np.float32), rng.random(4000).astype(np.float32)))
+    P.freeze_evm_net(0)
+    params = [p for p in P.net.parameters() if p.requires_grad]
+    opt = torch.optim.LBFGS(params, lr=0.5, max_iter=8, history_size=8, line_search_fn="strong_wolfe")
+    losses = []
+
+    def closure():
+        opt.zero_grad()
+        loss, _ = P.fwd_computing_loss_2d()
+        loss.backward()
+        losses.append(float(loss.detach()))
+        return loss
+    for _ in range(3):
+        opt.step(closure)
+    assert len(losses) >= 6 and np.all(np.isfinite(losses))
+    assert min(losses[-3:]) < 0.6 * losses[0], losses
+    assert P.net._is_flat()                      # L-BFGS updates the parameters in place: the flat buffer the kernels read stays valid
