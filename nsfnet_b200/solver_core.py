@@ -130,6 +130,7 @@ class SolverBase:
         self.ddp_compat = False
         self.store_residuals = True
         self.x_b = self.x_f = None
+        self.graph_replays = 0       # iterations executed as a CUDA-graph replay (introspection)
         self._fused = False          # enable_fused_step(): device-resident Adam + CUDA-graph replay of the iteration
         self._fused_graph = True
         self._graphs = {}
@@ -541,6 +542,7 @@ class SolverBase:
         for k, v in outs.items():
             setattr(self, k, v)
         g.replay()
+        self.graph_replays += 1
         return self.loss
 
     def get_runtime_stats(self, epoch_id, num_epoch):

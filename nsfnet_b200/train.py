@@ -115,6 +115,7 @@ def main(argv=None):
                 PINN.evaluate(*eval_data)
         if PINN.tb_writer is not None:
             PINN.tb_writer.close()
+        main.last_solver = PINN          # for callers that drive main() in-process (tests)
     finally:
         if "PINN" in locals():
             PINN.release_graphs()
