@@ -35,6 +35,7 @@
 #include "nsf_internal.h"
 #include "nsf_tc.cuh"
 #include "nsf_math.cuh"
+#include <cstdlib>
 
 using namespace nsftc;
 
@@ -78,6 +79,7 @@ struct UArgs {
   float* stash;          // [grid][NS][L][P][KP][4]
   float* scratch;        // gradient rows [grid][gs_row]
   int n_pairs;
+  int multi;             // merge the MMAs of slots whose operands are ready together (N = 64 / 96)
   long long* dbg;        // optional [grid][16 warps][16] cycle counters (nsf_get_stage_cycles)
 };
 
@@ -122,8 +124,12 @@ __host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t la
 // address field never carries into the LBO field.
 __host__ __device__ constexpr uint32_t lbo_field(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
 
+// `nslots` consecutive slots (their operands are ready at the same time) are contracted by ONE set of MMAs with N = 32 * nslots:
+// the B operand of slot k+1 lies SLOT bytes behind slot k's, which is what the leading-byte-offset of the MN-major layout
+// expresses (the next 32 columns of n), and the D slots are adjacent TMEM columns.  The 4 KB weight operand -- what an
+// N = 32 MMA spends 36 of its 43 cycles fetching -- is then read once for 16 or 24 points (36 + N/4 cycles, measured).
 template <int L>
-__device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, int slot, uint32_t wbuf, uint32_t leader, int half) {
+__device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, int slot, int nslots, uint32_t wbuf, uint32_t leader, int half) {
   const uint32_t wa4 = sb4 + (wbuf ? (WBUF >> 4) : 0u);
   const uint32_t r4 = sb4 + (uint32_t)((OFF_SLOT + slot * SLOT) >> 4);
   const uint32_t d_col = tmem + (uint32_t)((L - 1) * NW + slot * NCOL);
@@ -132,10 +138,10 @@ __device__ __forceinline__ void issue_main(uint32_t sb4, uint32_t tmem, int s, i
     // same-sign sums).  Issue the 2^-11-sized correction products first, while the accumulator is still small,
     // and the hi*hi products last: 10 full-magnitude accumulations per layer instead of 30.
     // The output layer (s = L) has 3 real rows: M = 64 halves the operand fetch of its MMAs.
-    const uint32_t idesc = (s == L) ? idesc_tf32(64, NCOL, 0, 1) : idesc_tf32(128, NCOL, 0, 1);
+    const uint32_t idesc = (s == L) ? idesc_tf32(64, NCOL * nslots, 0, 1) : idesc_tf32(128, NCOL * nslots, 0, 1);
     constexpr uint32_t AHI = desc_hi(W_SBO), BHI = desc_hi_t(R_ATOM, 1);
     const uint32_t ah0 = wa4 + lbo_field(128), al0 = ah0 + (IMG >> 4);
-    const uint32_t bh0 = r4 + lbo_field(1024), bl0 = bh0 + (RB >> 4);
+    const uint32_t bh0 = r4 + lbo_field(SLOT), bl0 = bh0 + (RB >> 4);
     if (half == 0) {
 #pragma unroll
       for (int ks = 0; ks < KP / 8; ++ks) {
@@ -292,6 +298,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     uint32_t rphases = 0;                  // bit = slot: parity to wait for
     bool pre_ok = false;                   // the next slot's `ready` phase was already seen complete
     uint32_t stage_ctr = 0;                // MMA stages issued so far (selects the weight buffer)
+    uint32_t cphases = 0;                  // bit = slot: parity the slot's `mbar` completes next (multi mode throttle)
+    uint64_t* q_bar1 = nullptr; uint64_t* q_bar2 = nullptr;   // completion barriers of the last two sets issued
+    uint32_t q_par1 = 0, q_par2 = 0;
     long long icnt[5] = {0, 0, 0, 0, 0};   // -, issue, operand (+ weight) wait, -, stage-slots
     long long swait[2 * MAXL];             // operand wait per stage (diagnostic rows of the two non-epilogue warps)
 #pragma unroll
@@ -300,6 +309,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
 #pragma unroll 1
       for (int s = 1; s < NSTAGE; ++s) {
         const uint32_t b = stage_ctr & 1u;
+        if (a.multi) {
+          int slot = 0;
+#pragma unroll 1
+          while (slot < NS) {
+            long long t0 = 0, t1 = 0;
+            if (DBG) t0 = clock64();
+            mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u);
+            // Throttle: at most one set queued behind the one that executes.  Issuing any earlier buys nothing (the sets run in
+            // order) and every cycle of patience lets another slot's operands arrive, i.e. a wider, cheaper set.
+            if (a.multi >= 2 && q_bar2 != nullptr) mbar_wait(q_bar2, q_par2);
+            int n = 1;
+            while (slot + n < NS && mbar_test_wait(&misc->ready[slot + n], (rphases >> (slot + n)) & 1u)) ++n;
+            rphases ^= ((1u << n) - 1u) << slot;
+            if (DBG) {
+              t1 = clock64(); icnt[2] += t1 - t0;
+#pragma unroll
+              for (int i = 1; i < 2 * MAXL; ++i) if (i == s) swait[i] += t1 - t0;
+              t0 = t1;
+            }
+            tc_fence_after();
+            issue_main<L>(smem_base >> 4, tmem, s, slot, n, b, leader, 0);
+            issue_main<L>(smem_base >> 4, tmem, s, slot, n, b, leader, 1);
+            for (int i = 0; i < n; ++i) mma_commit_elect(&misc->mbar[slot + i], leader);
+            q_bar2 = q_bar1; q_par2 = q_par1;
+            q_bar1 = &misc->mbar[slot + n - 1]; q_par1 = (cphases >> (slot + n - 1)) & 1u;
+            cphases ^= ((1u << n) - 1u) << slot;
+            if (slot + n == NS) mma_commit_elect(&misc->wfree[b], leader);
+            if (s > L) {
+              for (int i = 0; i < n; ++i) {
+                issue_wgrad<L>(smem_base >> 4, tmem, s, slot + i, (pr % FLUSH) == 0 && slot + i == 0, leader);
+                mma_commit_elect(&misc->wdone[slot + i], leader);
+              }
+            }
+            __syncwarp();
+            if (DBG) { t1 = clock64(); icnt[1] += t1 - t0; icnt[4] += n; icnt[3] += (n > 1); }
+            slot += n;
+          }
+        } else {
 #pragma unroll
         for (int slot = 0; slot < NS; ++slot) {     // unrolled: the slot's operand descriptors are constants + smem_base
           long long t0 = 0, t1 = 0;
@@ -317,7 +364,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           if (DBG) { t1 = clock64(); icnt[0] += t1 - t0; t0 = t1; }
           // dgrad first: the epilogue of the next stage only needs its result; the weight-gradient MMAs get their own
           // completion barrier (they read the C images, which that epilogue rewrites last)
-          issue_main<L>(smem_base >> 4, tmem, s, slot, b, leader, 0);
+          issue_main<L>(smem_base >> 4, tmem, s, slot, 1, b, leader, 0);
           // probe the next slot's operands while this slot's MMAs queue up: a blocking poll after the last MMA costs
           // the pipe its ~4-deep queue (150-200 cycles per stage and slot, round-1 cycle counters)
           {
@@ -325,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             pre_ok = mbar_test_wait(&misc->ready[nslot], (rphases >> nslot) & 1u);
             if (pre_ok) tc_fence_after();     // the fence of the next slot, overlapped with this slot's queued MMAs
           }
-          issue_main<L>(smem_base >> 4, tmem, s, slot, b, leader, 1);
+          issue_main<L>(smem_base >> 4, tmem, s, slot, 1, b, leader, 1);
           mma_commit_elect(&misc->mbar[slot], leader);
           if (slot == NS - 1) mma_commit_elect(&misc->wfree[b], leader);
           if (s > L) {
@@ -334,6 +381,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
           }
           __syncwarp();
           if (DBG) { t1 = clock64(); icnt[1] += t1 - t0; icnt[4] += 1; }
+        }
         }
         ++stage_ctr;
       }
@@ -823,6 +871,10 @@ int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_param
   a.stash = train ? s->stash : nullptr;
   a.scratch = train ? k.scratch : nullptr;
   a.n_pairs = (int)((k.n + NS * P - 1) / (NS * P));
+  {
+    static const int multi_env = [] { const char* v = getenv("NSF_UMMA_MULTI"); return v ? atoi(v) : 0; }();
+    a.multi = multi_env;
+  }
   a.dbg = s->dbg_on ? s->dbg : nullptr;
   int grid = a.n_pairs < s->grid ? a.n_pairs : s->grid;
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }
