@@ -85,7 +85,7 @@ struct UArgs {
 
 struct Misc {
   uint64_t mbar[NS];     // "done": the slot's MMAs have completed (tcgen05.commit)
-  uint64_t wbar[2];      // (diagnostics only)
+  uint64_t wbar[2];      // issue throttle of the merged-set mode: set i commits to wbar[i & 1] (tcgen05.commit)
   uint64_t ready[NS];    // the slot's operands are written and its previous results consumed (one arrival per epilogue warp);
                          // ready[0] also carries the stage's weight image (producer arrival + TMA complete_tx): every
                          // mbarrier poll costs 200+ cycles while the MMAs saturate shared memory, so the issuer polls once
@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
       mbar_init(&misc->ready[i], NEPI / 32 + (i == 0 ? 1 : 0));
     }
     mbar_init(&misc->wfree[0], 1); mbar_init(&misc->wfree[1], 1);
+    mbar_init(&misc->wbar[0], 1); mbar_init(&misc->wbar[1], 1);
     mbar_fence_init();
   }
   // zero the operand slots once (the M = 128 operand fetch reads 48 rows past the 80 real ones) and the loss sums
@@ -298,9 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
     uint32_t rphases = 0;                  // bit = slot: parity to wait for
     bool pre_ok = false;                   // the next slot's `ready` phase was already seen complete
     uint32_t stage_ctr = 0;                // MMA stages issued so far (selects the weight buffer)
-    uint32_t cphases = 0;                  // bit = slot: parity the slot's `mbar` completes next (multi mode throttle)
-    uint64_t* q_bar1 = nullptr; uint64_t* q_bar2 = nullptr;   // completion barriers of the last two sets issued
-    uint32_t q_par1 = 0, q_par2 = 0;
+    uint32_t set_ctr = 0;                  // MMA sets issued so far (merged-set mode)
     long long icnt[5] = {0, 0, 0, 0, 0};   // -, issue, operand (+ weight) wait, -, stage-slots
     long long swait[2 * MAXL];             // operand wait per stage (diagnostic rows of the two non-epilogue warps)
 #pragma unroll
@@ -318,8 +317,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             mbar_wait(&misc->ready[slot], (rphases >> slot) & 1u);
             // Throttle: at most one set queued behind the one that executes.  Issuing any earlier buys nothing (the sets run in
             // order) and every cycle of patience lets another slot's operands arrive, i.e. a wider, cheaper set.
-            if (a.multi >= 2 && q_bar2 != nullptr) mbar_wait(q_bar2, q_par2);
+            // (own barriers, committed alternately: the slots' `mbar`s can complete twice between two looks of this warp)
+            if (a.multi >= 2 && set_ctr >= 2) mbar_wait(&misc->wbar[set_ctr & 1u], ((set_ctr - 2) >> 1) & 1u);
             int n = 1;
+            if (a.multi == 3 && slot == 0) { mbar_wait(&misc->ready[1], (rphases >> 1) & 1u); n = 2; }   // static pairing {0,1} + {2}
             while (slot + n < NS && mbar_test_wait(&misc->ready[slot + n], (rphases >> (slot + n)) & 1u)) ++n;
             rphases ^= ((1u << n) - 1u) << slot;
             if (DBG) {
@@ -332,9 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet_kernel(const UArgs a
             issue_main<L>(smem_base >> 4, tmem, s, slot, n, b, leader, 0);
             issue_main<L>(smem_base >> 4, tmem, s, slot, n, b, leader, 1);
             for (int i = 0; i < n; ++i) mma_commit_elect(&misc->mbar[slot + i], leader);
-            q_bar2 = q_bar1; q_par2 = q_par1;
-            q_bar1 = &misc->mbar[slot + n - 1]; q_par1 = (cphases >> (slot + n - 1)) & 1u;
-            cphases ^= ((1u << n) - 1u) << slot;
+            if (a.multi >= 2) mma_commit_elect(&misc->wbar[set_ctr & 1u], leader);
+            ++set_ctr;
             if (slot + n == NS) mma_commit_elect(&misc->wfree[b], leader);
             if (s > L) {
               for (int i = 0; i < n; ++i) {
