@@ -31,8 +31,8 @@ EXEC_FLOPS_PER_PT = {"ev": 30 * 80 * 80 * 5 * 0.8 + 9840.0, "ns": 30 * 120 * 120
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture of
-# this command line (profiles/r1_umma_v7_1M_ncu_summary.txt); keyed by (workload, kernel path, points per GPU)
-NCU_TRAFFIC_BYTES = {("ev", 2, 1_000_000): 16.82e6 + 35.25e6}   # stash kept L2-resident (ld/st .cg): profiles/r1_umma_v7_dram_traffic.txt
+# this command line (profiles/r1_umma_v10_1M_ncu_summary.txt); keyed by (workload, kernel path, points per GPU)
+NCU_TRAFFIC_BYTES = {("ev", 2, 1_000_000): 17.10e6 + 32.02e6}   # stash kept L2-resident (ld/st .cg): profiles/r1_umma_v10_1M_ncu_summary.txt
 
 
 def read_peaks():
