@@ -157,6 +157,62 @@ __global__ void __launch_bounds__(128) time_kernel_t(long long* out /* [16] */) 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// B operand MN-major, descriptor layout type 1 (the jet kernel's R image: 128-byte rows of 32 columns n, 512-byte atoms
+// of 4 k-rows, the next 32 columns LBO bytes on): does a wider N amortise the fetch of the A operand here as well?
+template <int M, int N, int NM>
+__global__ void __launch_bounds__(128) time_kernel_mn(long long* out, uint32_t lbo_bytes) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  for (int i = tid; i < 55000; i += 128) *reinterpret_cast<float*>(smem + i * 4) = 0.001f * (float)(i & 63);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (warp == 0) {
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = idesc_gen(M, N, 0, 1);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 61440;     // A: 2 x 25600 (hi | lo); B: images of 10240 B, 40960 B apart
+    constexpr uint32_t AHI = desc_hi(2560);
+    const uint32_t BHI = ((512u >> 4) & 0x3FFF) | (1u << 14) | (1u << 29);
+    const uint32_t ah0 = desc_lo(a0, 128), al0 = desc_lo(a0 + 25600, 128);
+    const uint32_t bh0 = desc_lo(b0, lbo_bytes), bl0 = desc_lo(b0 + 10240, lbo_bytes);
+    for (int rep = 0; rep < 8; ++rep) {
+      __syncwarp();
+      const long long t0 = clock64();
+#pragma unroll
+      for (int i = 0; i < NM; ++i) {
+        const int ks = i % 10;
+        const uint32_t da = ks * (256 >> 4), db = ks * (1024 >> 4);
+        mma_tf32_elect2(tb, ((i / 10) & 1 ? al0 : ah0) + da, AHI, ((i / 10) & 1 ? bl0 : bh0) + db, BHI, idesc, i > 1, leader);
+      }
+      mma_commit_elect(&bar, leader);
+      const long long t1 = clock64();
+      mbar_wait(&bar, rep & 1);
+      const long long t2 = clock64();
+      if (tid == 0) { out[rep * 2] = t1 - t0; out[rep * 2 + 1] = t2 - t0; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+template <int M, int N, int NM>
+static void run_time_mn(uint32_t lbo, long long* d_t) {
+  CK(cudaFuncSetAttribute(time_kernel_mn<M, N, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  time_kernel_mn<M, N, NM><<<1, 128, 220 * 1024>>>(d_t, lbo);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("[mn] CUDA error: %s\n", cudaGetErrorString(e)); exit(2); }
+  long long t[16]; CK(cudaMemcpy(t, d_t, sizeof(t), cudaMemcpyDeviceToHost));
+  long long bi = 1LL << 60, bt = 1LL << 60;
+  for (int r = 2; r < 8; ++r) { if (t[2 * r] < bi) bi = t[2 * r]; if (t[2 * r + 1] < bt) bt = t[2 * r + 1]; }
+  printf("SS, B MN-major type 1 (LBO %5u) M=%3d N=%3d nmma=%3d : issue %6lld cyc, complete %6lld cyc (%.1f / MMA)\n", lbo, M, N, NM, bi, bt, (double)bt / NM);
+}
+
 template <int M, int N, int TS, int NM, int SAMED>
 static void run_time_t(const char* name, long long* d_t) {
   CK(cudaFuncSetAttribute(time_kernel_t<M, N, TS, NM, SAMED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -192,6 +248,18 @@ static void run_decode(const char* name, DecodeCfg c, float* d_out, std::vector<
 
 int main(int argc, char** argv) {
   CK(cudaSetDevice(0));
+  if (argc == 2 && !strcmp(argv[1], "mn")) {   // timing of MN-major (layout type 1) B operands only
+    long long* d_tm; CK(cudaMalloc(&d_tm, 16 * sizeof(long long)));
+    run_time_mn<128, 32, 30>(40960, d_tm);
+    run_time_mn<128, 64, 30>(40960, d_tm);
+    run_time_mn<128, 96, 30>(40960, d_tm);
+    run_time_mn<128, 64, 30>(10240, d_tm);
+    run_time_mn<128, 64, 30>(4096, d_tm);
+    run_time_mn<64, 32, 30>(40960, d_tm);
+    run_time_mn<64, 64, 30>(40960, d_tm);
+    printf("done\n");
+    return 0;
+  }
   if (argc == 9) {   // single decode: which mn ltype lbo sbo N M start   (one process per configuration: a bad descriptor faults)
     CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024));
     float* d_out1; CK(cudaMalloc(&d_out1, 2 * 128 * 256 * sizeof(float)));
