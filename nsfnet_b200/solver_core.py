@@ -36,7 +36,10 @@ def _dev_f32(a, device) -> torch.Tensor:
         t = a.detach()
     else:
         t = torch.as_tensor(np.asarray(a))
-    return t.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+    # a PINNED fp32 host tensor is copied asynchronously on the current stream (the kernels that read it are ordered behind the
+    # copy; the caller must not overwrite the buffer before the stream gets there); everything else is the reference's blocking copy
+    pinned = t.device.type == "cpu" and t.dtype == torch.float32 and t.is_pinned()
+    return t.to(device=device, dtype=torch.float32, non_blocking=pinned).reshape(-1).contiguous()
 
 
 def shard_bounds(total: int, rank: int, world_size: int):
