@@ -75,6 +75,8 @@ class PysicsInformedNeuralNetwork(SolverBase):
                 self.print_log(loss, losses, epoch_id, num_epoch)
             if self.rank == 0 and getattr(self, "checkpoints", True) and (epoch_id == 0 or epoch_id % 10000 == 0):
                 self.save("model_cavity_loop%d.pth" % epoch_id, N_HLayer=self.layers, N_neu=self.hidden_size, N_f=self.N_f)
+        if fused and self.is_distributed:
+            self.release_graphs()      # no captured NCCL kernels outlive the loop (a later destroy_process_group would wait for them)
 
     def freeze_evm_net(self, epoch_id):
         for p in self.net_1.parameters():

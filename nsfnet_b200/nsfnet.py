@@ -67,6 +67,8 @@ class PysicsInformedNeuralNetwork(SolverBase):
             if self.rank == 0 and getattr(self, "checkpoints", True) and epoch_id % 10000 == 0:
                 self.save("model_cavity_loop_%d.pth" % epoch_id, N_HLayer=self.layers, N_neu=self.hidden_size, N_f=self.N_f)
             epoch_id += 1
+        if fused and self.is_distributed:
+            self.release_graphs()      # no captured NCCL kernels outlive the loop (a later destroy_process_group would wait for them)
 
     def _save_dir(self, directory, N_HLayer, N_neu, N_f):
         nn = f"{N_HLayer}x{N_neu}_Nf{np.int32(N_f / 1000)}k"

@@ -77,7 +77,7 @@ def main():
         P.train(num_epoch=10, lr=1e-3)
         results[mode] = P.net.flat_params().clone()
         if mode == "fused_graph":
-            assert any(isinstance(v, tuple) for v in P._graphs.values())
+            assert P.graph_replays >= 8                                    # 10 epochs, the first two of the stage run eagerly
         both = [torch.empty_like(results[mode]) for _ in range(world)]
         dist.all_gather(both, results[mode])
         assert all(torch.equal(both[0], b) for b in both), mode            # replicas stay bit-identical
@@ -101,7 +101,7 @@ def main():
     assert torch.equal(torch.sort(cat[cat >= 0]).values, torch.arange(n_f, device="cuda"))      # one point per stratum, globally
     loss, _ = P.fwd_computing_loss_2d()
     assert np.isfinite(float(loss))
-    P.release_graphs()            # captured NCCL kernels must be gone before the process group is (destroy hangs otherwise)
+    assert not P._graphs          # solve_Adam released its captured NCCL kernels (a later destroy_process_group would hang on them)
     dist.barrier()
     if rank == 0:
         print(f"DDP_OK world={world} grad_rel={rel_g:.2e} loss_rel={rel_l:.2e} torch_vs_fused={d1:.2e} eager_vs_graph={d2:.2e}", flush=True)
