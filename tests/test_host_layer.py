@@ -72,3 +72,37 @@ def test_cavity_data_matches_reference_sets():
     dist = np.minimum(np.minimum(x, 1 - x), np.minimum(y, 1 - y)).ravel()
     assert np.all(np.diff(dist) > -2e-3)          # sorted by wall distance (to the discrete boundary set)
     assert w[0] > w[-1]
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in nsfnet_b200/_capi.py against include/nsf_b200.h as the C compiler lays it out (sizes and
+    field offsets): the boundary is plain C, so any binding -- cgo, JNI, cffi -- sees exactly these numbers."""
+    import subprocess
+    from nsfnet_b200 import _capi
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "nsf_b200.h"
+#define F(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("NsfNetDesc %zu\nNsfPhysics %zu\nNsfDataBlock %zu\nNsfAdamDev %zu\n", sizeof(NsfNetDesc), sizeof(NsfPhysics), sizeof(NsfDataBlock), sizeof(NsfAdamDev));
+  F(NsfPhysics, inv_Re); F(NsfPhysics, eq4_weight); F(NsfPhysics, flags); F(NsfPhysics, alpha_evm_init); F(NsfPhysics, n_f_norm);
+  F(NsfDataBlock, p); F(NsfDataBlock, n); F(NsfDataBlock, cu); F(NsfDataBlock, cp);
+  F(NsfAdamDev, lr); F(NsfAdamDev, grad_scale); F(NsfAdamDev, step);
+  printf("NSF_LOSS_SLOTS %d\nNSF_MAX_BLOCKS %d\nNSF_VTM_FROM_E %u\n", NSF_LOSS_SLOTS, NSF_MAX_BLOCKS, NSF_VTM_FROM_E);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines())
+    for name, cls in (("NsfNetDesc", _capi.NsfNetDesc), ("NsfPhysics", _capi.NsfPhysics), ("NsfDataBlock", _capi.NsfDataBlock),
+                      ("NsfAdamDev", _capi.NsfAdamDev)):
+        assert int(out[name]) == ctypes.sizeof(cls), name
+    for key, val in out.items():
+        if "." in key:
+            struct, field = key.split(".")
+            assert int(val) == getattr(getattr(_capi, struct), field).offset, key
+    assert int(out["NSF_LOSS_SLOTS"]) == _capi.NSF_LOSS_SLOTS and int(out["NSF_MAX_BLOCKS"]) == _capi.NSF_MAX_BLOCKS
+    assert int(out["NSF_VTM_FROM_E"]) == _capi.NSF_VTM_FROM_E
