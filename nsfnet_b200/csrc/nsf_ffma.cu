@@ -81,7 +81,16 @@ __global__ void nsf_finalize_kernel(NsfNetGeom g, const float* __restrict__ scra
   const int col = is_loss ? g.gs_loss() + (i - np) : map[i];
   const long long stride = g.gs_row();
   double acc = 0.0;
-  for (int r = 0; r < rows; ++r) acc += (double)scratch[r * stride + col];
+  const float* src = scratch + col;
+  int r = 0;
+  for (; r + 8 <= rows; r += 8) {          // eight independent loads in flight, summed in row order (fixed => bitwise reproducible)
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + (long long)(r + k) * stride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += (double)v[k];
+  }
+  for (; r < rows; ++r) acc += (double)__ldcg(src + (long long)r * stride);
   if (is_loss) loss_parts[i - np] = (float)acc;
   else grad[i] = (float)acc;
 }
