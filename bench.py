@@ -11,8 +11,11 @@ N > 1).  `--workload ns` runs BASELINE config[1] (NSFnet 4x120, Re=1000, 1M poin
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline` (dominant kernel, timed by
 CUDA events inside the library on the launching stream), `cpu_baseline` (the autograd port of the
-reference timed on this box's host cores), `adam_steps_per_s`, `e2e` (public solver API with host
-buffers), `clocks`, `gpu_launches`.
+reference timed on this box's host cores), `e2e` (public solver API with pinned HOST buffers: H2D of
+the points and D2H of the loss inside every timed step), `clocks`, `gpu_launches`, and metric (ii) of
+BASELINE.json: `adam_steps_per_s` (fused iteration: nsf_step + device-resident Adam, one CUDA graph
+replay), `adam_steps_per_s_torch_optim_loop` (the reference's loop body on the same kernels) and
+`adam_small_batch` (both again at the shipped 120 000 points per GPU, where launch overhead decides).
 """
 import argparse
 import json
