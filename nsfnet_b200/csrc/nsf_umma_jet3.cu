@@ -210,18 +210,17 @@ __device__ __forceinline__ void zbar_from(const float4 st, const float ab[4], fl
 
 // The weight-gradient accumulator of layer l (TMEM lane = j, columns TM_DW + (l % NDW)*80 + k) of the tile group just
 // finished -> added to this CTA's gradient row (L2 resident).  A warp covers its 32 neurons for every fourth 8-column
-// chunk (subs 0, 1: three chunks, subs 2, 3: two); all loads are in flight before the first add.
+// chunk (subs 0, 1: three chunks, subs 2, 3: two).  The additions are vector reductions (red.global.add.v4.f32): nothing is
+// read back, and since every element of the row is only ever touched by ONE thread, in program order, the sums are exact
+// and bit-reproducible (a read-modify-write cost 2400 cycles per flush, this costs 765).
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void flush_dw(const NsfNetGeom& g, float* grow, uint32_t tmem, const Epi& e, int l, bool first) {
   const uint32_t src = tmem + e.lane_addr + TM_DW + (uint32_t)((l % NDW) * NW) + (uint32_t)(e.sub * 8);
-  float4* dst = reinterpret_cast<float4*>(grow + g.gs_w(l) + (size_t)(e.active ? e.j : 0) * g.HP + e.sub * 8);
+  float* dst = grow + g.gs_w(l) + (size_t)(e.active ? e.j : 0) * g.HP + e.sub * 8;
   const bool third = e.sub < 2;                      // chunk index sub + 8 exists only for sub < 2
   float v[3][8];
-  float4 p[3][2];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    p[c][0] = p[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!first && e.active && (c < 2 || third)) { p[c][0] = __ldcg(dst + c * 8); p[c][1] = __ldcg(dst + c * 8 + 1); }
-  }
   tmem_ld8(src, v[0]);
   tmem_ld8(src + 32, v[1]);
   if (third) tmem_ld8(src + 64, v[2]);               // warp-uniform
@@ -230,8 +229,14 @@ __device__ __forceinline__ void flush_dw(const NsfNetGeom& g, float* grow, uint3
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (c < 2 || third) {
-        __stcg(dst + c * 8, make_float4(v[c][0] + p[c][0].x, v[c][1] + p[c][0].y, v[c][2] + p[c][0].z, v[c][3] + p[c][0].w));
-        __stcg(dst + c * 8 + 1, make_float4(v[c][4] + p[c][1].x, v[c][5] + p[c][1].y, v[c][6] + p[c][1].z, v[c][7] + p[c][1].w));
+        float* d = dst + c * 32;
+        if (first) {     // the row is this CTA's own: the first group overwrites, later groups add without reading (no L2 round trip)
+          __stcg(reinterpret_cast<float4*>(d), make_float4(v[c][0], v[c][1], v[c][2], v[c][3]));
+          __stcg(reinterpret_cast<float4*>(d) + 1, make_float4(v[c][4], v[c][5], v[c][6], v[c][7]));
+        } else {
+          red_add_v4(d, v[c][0], v[c][1], v[c][2], v[c][3]);
+          red_add_v4(d + 4, v[c][4], v[c][5], v[c][6], v[c][7]);
+        }
       }
     }
   }
