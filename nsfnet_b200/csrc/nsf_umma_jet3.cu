@@ -1,19 +1,19 @@
 // tcgen05 jet kernel, third generation ("tile-major, weights in tensor memory"): hidden = 80, 2..6 hidden layers.
 //
-// Same tile-major structure, thread mapping, operand images and 3xTF32 ordering as nsf_umma_jet.cu (three 8-point tile
-// slots in flight, TMEM lane = neuron, column = 4*point + stream, mbarrier-only steady state), with ONE change of plan that
-// round-1 profiling asked for (profiles/r1_umma_v10_1M_ncu_summary.txt: tensor pipe 43 % active, the N = 32 MMAs spend
+// Same tile-major structure, thread mapping, operand images and 3xTF32 ordering as nsf_umma_jet.cu (8-point tile slots in
+// flight -- four here --, TMEM lane = neuron, column = 4*point + stream, mbarrier-only steady state), with ONE change of plan
+// that round-1 profiling asked for (profiles/r1_umma_v10_1M_ncu_summary.txt: tensor pipe 43 % active, the N = 32 MMAs spend
 // 43 cycles fetching a 4 KB weight operand from shared memory for 16 cycles of math):
 //   * the weights of the current stage live in TENSOR MEMORY (A operand from TMEM: 17.6 cycles per N = 32 MMA instead of
-//     43, profiles/r1_probe_mma_timing.txt).  The 160 columns [W_hi | W_lo] are written by the epilogue warps themselves
-//     (each thread its neuron's row quarter: 10 LDG.128 from the L2-resident image + 5 tcgen05.st) right after the last
-//     slot's MMAs of the previous stage have completed, so one buffer is enough; no TMA producer, no shared-memory weight
-//     buffers;
+//     43, profiles/r1_probe_mma_timing.txt).  A producer lane TMA-stages the stage image (rows hi[80] | lo[80], padded to 164
+//     floats so that the LDS.128 of a column are conflict free) into ONE shared-memory buffer; the epilogue warps copy it into
+//     the 160 TMEM columns (each thread its neuron's row quarter: 10 LDS.128 + 5 tcgen05.st) right after the last slot's MMAs
+//     of the previous stage have completed, so one TMEM buffer is enough; the issuer waits for `wfull` before a stage's first MMA;
 //   * the tensor-memory columns for it come from the weight-gradient accumulators: a layer's dW is accumulated over the
-//     three slots of ONE tile group only, then added to the CTA's gradient row in L2 (fp32, by the thread that owns the
-//     neuron) -- three rotating 80-column accumulators instead of five persistent ones.  That also bounds the number of
-//     truncating tensor-core accumulations per value at 36.
-// TMEM map: [0,160) weights hi | lo, [160,400) three dW accumulators, [400,496) the three D slots.
+//     slots of ONE tile group only, then added to the CTA's gradient row in L2 by vector reductions (see flush_dw) -- two
+//     rotating 80-column accumulators instead of five persistent ones.  That also bounds the number of truncating tensor-core
+//     accumulations per value at 48.
+// TMEM map: [0,160) weights hi | lo, [160,320) two rotating dW accumulators, [320,448) the four D slots.
 #include "nsf_internal.h"
 #include "nsf_tc.cuh"
 #include "nsf_math.cuh"
@@ -24,7 +24,7 @@ namespace {
 
 constexpr int KP = 80;            // hidden width handled by this kernel
 constexpr int P = 8;              // points per tile slot
-constexpr int NS = 3;             // tile slots in flight
+constexpr int NS = 4;             // tile slots in flight (shared memory has room for four once the weights live in tensor memory)
 constexpr int NCOL = 4 * P;       // MMA N of the forward / dgrad contractions
 constexpr int NW = 80;            // MMA N of the weight-gradient contraction (columns of dW_l)
 constexpr int MAXL = 6;
@@ -34,9 +34,9 @@ constexpr int NWARPS = 4 * NSUB - 1;   // warps 4*sub + q, q = 0..2 epilogue; wa
 constexpr int NTHREADS = NWARPS * 32;  // 480
 constexpr int NEPI = 3 * NSUB * 32;    // 384 epilogue threads
 constexpr int ISSUER_WARP = 3;
-constexpr int NDW = 3;            // rotating weight-gradient accumulators
+constexpr int NDW = 2;            // rotating weight-gradient accumulators
 
-constexpr uint32_t TM_W = 0, TM_DW = 160, TM_D = TM_DW + NDW * NW;   // 0, 160, 400
+constexpr uint32_t TM_W = 0, TM_DW = 160, TM_D = TM_DW + NDW * NW;   // 0, 160, 320
 static_assert(TM_D + NS * NCOL <= 512, "tensor memory");
 constexpr int WROW = 164;                       // floats per image row: hi[80] | lo[80] | 4 pad (quarter-warp LDS.128 of a column: 8 bank groups)
 constexpr int WIMG_FLOATS = KP * WROW;          // one stage image in global memory
@@ -48,8 +48,8 @@ constexpr uint32_t RB = (KP / 4) * R_ATOM;      // 10240: one R image
 constexpr uint32_t SLOT = 4 * RB;                // 40960: R hi, R lo (z-bar or activations), RA hi, RA lo (activations of the layer below)
 constexpr uint32_t OFF_SLOT = 0;
 constexpr uint32_t OFF_WS = OFF_SLOT + NS * SLOT;    // 122880: two staging buffers for the stage images (TMA destination)
-constexpr uint32_t OFF_MISC = OFF_WS + 2 * WIMG_BYTES;  // 227840
-constexpr uint32_t MISC = 3072;
+constexpr uint32_t OFF_MISC = OFF_WS + WIMG_BYTES;      // one staging buffer: a stage lasts several TMA latencies
+constexpr uint32_t MISC = 4096;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;
 static_assert(OFF_SLOT % 1024 == 0 && SLOT % 1024 == 0, "R images must keep the 512-byte swizzle phase");
 static_assert(SMEM_BYTES <= 232448 && WIMG_BYTES % 16 == 0, "shared memory");
@@ -345,10 +345,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet3_kernel(const UArgs 
       const long long total = (long long)my_pairs * (NSTAGE - 1);
       int img = 0;
       for (long long i = 0; i < total; ++i) {
-        const int b = (int)(i & 1);
-        if (i >= 2) mbar_wait(&misc->wsfree[b], (uint32_t)(((i >> 1) - 1) & 1));
-        mbar_expect_tx(&misc->wsfull[b], WIMG_BYTES);
-        tma_bulk_g2s(smem + OFF_WS + (size_t)b * WIMG_BYTES, a.wimg + (size_t)img * WIMG_FLOATS, WIMG_BYTES, &misc->wsfull[b]);
+        if (i >= 1) mbar_wait(&misc->wsfree[0], (uint32_t)((i - 1) & 1));
+        mbar_expect_tx(&misc->wsfull[0], WIMG_BYTES);
+        tma_bulk_g2s(smem + OFF_WS, a.wimg + (size_t)img * WIMG_FLOATS, WIMG_BYTES, &misc->wsfull[0]);
         if (++img == NSTAGE - 1) img = 0;
       }
     }
@@ -383,12 +382,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nsf_umma_jet3_kernel(const UArgs 
     bool more_groups = false, first_group = true;                  // set by the group loop below, read by stage_step
     uint32_t wstage = 0;                                           // MMA stages whose weights this warp has moved to tensor memory
     auto weights_to_tmem = [&]() {
-      const uint32_t b = wstage & 1u;
-      mbar_wait(&misc->wsfull[b], (wstage >> 1) & 1u);
-      load_weights(smem + OFF_WS + (size_t)b * WIMG_BYTES, e, tmem);
+      mbar_wait(&misc->wsfull[0], wstage & 1u);
+      load_weights(smem + OFF_WS, e, tmem);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&misc->wfull); mbar_arrive(&misc->wsfree[b]); }
+      if (lane == 0) { mbar_arrive(&misc->wfull); mbar_arrive(&misc->wsfree[0]); }
       ++wstage;
     };
     if (my_pairs > 0) weights_to_tmem();                           // weights of the first MMA stage
