@@ -46,21 +46,27 @@ class PysicsInformedNeuralNetwork(SolverBase):
         return self.eq3_pred
 
     # ev :440-487
-    def solve_Adam(self, loss_func, num_epoch=1000, batchsize=None, scheduler=None):
+    def solve_Adam(self, loss_func, num_epoch=1000, batchsize=None, scheduler=None, start_epoch=0):
+        """``start_epoch`` (extension): continue a stage from a ``load_checkpoint`` state -- the epoch-0 optimizer reset is
+        skipped and the loop runs epochs ``start_epoch .. num_epoch-1``."""
         if not hasattr(self, "cumulative_start_time"):
             self.cumulative_start_time = time.time()
         self._epoch_start_wall = time.time()
         if not hasattr(self, "log_interval"):
             self.log_interval = 100
-        self.freeze_evm_net(0)
+        if not start_epoch:
+            self.freeze_evm_net(0)
         fused = self._fused and loss_func == self.fwd_computing_loss_2d
-        for epoch_id in range(num_epoch):
+        if fused and start_epoch and self._adam is None:
+            self._adam_reset()
+        for epoch_id in range(start_epoch, num_epoch):
             self.global_step += 1
             if epoch_id != 0 and epoch_id % 10000 == 0:
                 self.defreeze_evm_net(epoch_id)
             if (epoch_id - 1) % 10000 == 0:
                 self.freeze_evm_net(epoch_id)
             if fused:
+                self._sync_fused_lr()
                 loss = self._fused_step_replayable()
                 losses = [self.loss_e, self.loss_b]
             else:

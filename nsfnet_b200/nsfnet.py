@@ -42,10 +42,10 @@ class PysicsInformedNeuralNetwork(SolverBase):
         return self.eq3_pred
 
     # NSFnet :240-278
-    def solve_Adam(self, loss_func, num_epoch=1000, batchsize=None, scheduler=None):
+    def solve_Adam(self, loss_func, num_epoch=1000, batchsize=None, scheduler=None, start_epoch=0):
         import time
         self._epoch_start_wall = time.time()
-        epoch_id = 0
+        epoch_id = start_epoch
         fused = self._fused and loss_func == self.fwd_computing_loss_2d
         if fused:                      # ONE Adam for the whole run (NSFnet :76-79); only the learning rate follows the stage
             if self._adam is None:
@@ -53,6 +53,7 @@ class PysicsInformedNeuralNetwork(SolverBase):
             self._adam_set_lr(self.opt.param_groups[0]["lr"])
         while epoch_id < num_epoch:
             if fused:
+                self._sync_fused_lr()
                 loss = self._fused_step_replayable()
                 losses = [self.loss_e, self.loss_b]
             else:

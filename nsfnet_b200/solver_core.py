@@ -59,14 +59,19 @@ class _StepFn(torch.autograd.Function):
         loss = solver._launch_step()
         ctx.solver = solver
         ctx.n_in = len(params)
+        ctx.eval_id = solver._eval_id          # the flat gradient of THIS evaluation lives in solver._gbuf until the next one
+        ctx.slices = solver._param_slices
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         s = ctx.solver
+        if ctx.eval_id != s._eval_id:
+            raise RuntimeError("loss.backward() after a later loss evaluation: the kernel keeps ONE gradient buffer per solver "
+                               "(call backward() before the next fwd_computing_loss_2d / neural_net_equations on the training set)")
         scaled = s._gbuf * gout
         outs = []
-        for (net_id, off, numel, shape, req) in s._param_slices:
+        for (net_id, off, numel, shape, req) in ctx.slices:
             if req:
                 base = 0 if net_id == 0 else s._n_main
                 outs.append(scaled[base + off: base + off + numel].view(shape))
@@ -138,6 +143,8 @@ class SolverBase:
         self._fused_graph = True
         self._graphs = {}
         self._adam = None
+        self._eval_id = 0            # bumped by every nsf_step launch (guards _StepFn.backward against a stale gradient buffer)
+        self._resid = self._e = self._vis = None
 
         self.net = self.initialize_NN(num_ins=num_ins, num_outs=num_outs, num_layers=layers, hidden_size=hidden_size).to(self.device)
         self.net_1 = None
@@ -186,6 +193,7 @@ class SolverBase:
         s, e = self._shard(total)
         self.x_b, self.y_b, self.u_b, self.v_b = [_dev_f32(np.asarray(a)[s:e], self.device) for a in X[:4]]
         self._n_b_global = total
+        self._graphs = {}            # captured iterations bake in the old buffer addresses
         if self.rank == 0 and self.verbose:
             print(f"GPU {self.rank}: Processing {e - s} boundary points out of {total} total")
 
@@ -205,9 +213,11 @@ class SolverBase:
             self.eq_weights = None
         self._n_f_global = total
         n = self.x_f.numel()
-        self._resid = torch.empty(4 * n, dtype=torch.float32, device=self.device)
-        self._e = torch.empty(n, dtype=torch.float32, device=self.device)
-        self._vis = torch.empty(n, dtype=torch.float32, device=self.device)
+        if self._resid is None or self._resid.numel() != 4 * n:      # output buffers: once per shard size, not per call
+            self._resid = torch.empty(4 * n, dtype=torch.float32, device=self.device)
+            self._e = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._vis = torch.empty(n, dtype=torch.float32, device=self.device)
+        self._graphs = {}            # captured iterations bake in the old point / lag-state addresses
         if self.rank == 0 and self.verbose:
             print(f"GPU {self.rank}: Processing {e - s} equation points out of {total} total")
         if self.HAS_EVM:
@@ -246,6 +256,7 @@ class SolverBase:
         self.supervision_has_data = False
         self.supervision_enabled = False
         self._n_s_global = self._n_ps_global = 0
+        self._graphs = {}
 
     def set_supervised_data(self, data):
         if data is None:
@@ -263,6 +274,7 @@ class SolverBase:
         self._n_ps_global = int(np.isfinite(p).sum()) if p is not None else 0
         self.supervision_has_data = True
         self.supervision_enabled = self.alpha_s != 0.0
+        self._graphs = {}
 
     def set_supervised_loss_weight(self, weight):
         self.alpha_s = float(weight)
@@ -323,6 +335,7 @@ class SolverBase:
         self._vtm = (p["alpha"] * e.abs()).reshape(-1).contiguous()
 
     def _launch_step(self):
+        self._eval_id += 1
         net, net1 = self.net, self.net_1
         pm = net.flat_params()
         pe = net1.flat_params() if net1 is not None else None
@@ -451,12 +464,21 @@ class SolverBase:
         return self.neural_net_u(x, y)
 
     # ---- training loops ----------------------------------------------------------------------
-    def train(self, num_epoch=1, lr=1e-4, optimizer=None, scheduler=None, batchsize=None):
+    def train(self, num_epoch=1, lr=1e-4, optimizer=None, scheduler=None, batchsize=None, start_epoch=0):
         if self.opt is not None:
             self.opt.param_groups[0]["lr"] = lr
         else:
             self.opt = torch.optim.Adam(params=self.net.parameters(), lr=lr)
+        if start_epoch:
+            return self.solve_Adam(self.fwd_computing_loss_2d, num_epoch, batchsize, scheduler, start_epoch=start_epoch)
         return self.solve_Adam(self.fwd_computing_loss_2d, num_epoch, batchsize, scheduler)
+
+    def _sync_fused_lr(self):
+        """A scheduler (or the caller) may have changed ``self.opt``'s learning rate: the fused iteration reads it from a
+        device scalar, so write it there (a fill on the same buffer -- captured graphs stay valid)."""
+        lr = float(self.opt.param_groups[0]["lr"])
+        if self._adam is not None and lr != getattr(self, "_fused_lr", None):
+            self._adam_set_lr(lr)
 
     # ---- fused iteration (SURVEY 8f row 1) ---------------------------------------------------
     def enable_fused_step(self, enabled=True, graph=True):
@@ -489,6 +511,7 @@ class SolverBase:
 
     def _adam_set_lr(self, lr):
         self._adam["state"][0:1].fill_(float(lr))
+        self._fused_lr = float(lr)
 
     def adam_step_count(self) -> int:
         return int(self._adam["state"].view(torch.int32)[5].item()) if self._adam is not None else 0
@@ -511,9 +534,13 @@ class SolverBase:
     def _graph_key(self):
         ptr = lambda t: 0 if t is None else t.data_ptr()
         trainable = self.HAS_EVM and any(p.requires_grad for p in self.net_1.parameters())
-        return (ptr(self.x_f), ptr(self.y_f), self.x_f.numel(), ptr(self.eq_weights), ptr(self.x_b), ptr(self._vtm), self._vtm_pending is None,
-                ptr(self.x_s), ptr(self.p_s), self.supervision_enabled, float(self.alpha_evm), float(self.alpha_b), float(self.alpha_e),
-                float(self.alpha_s), float(self.coord_scale), trainable, self.store_residuals, self._n_f_global,
+        return (ptr(self.x_f), ptr(self.y_f), self.x_f.numel(), ptr(self.eq_weights), ptr(self._vtm), self._vtm_pending is None,
+                ptr(self._resid), ptr(self._e), ptr(self._vis), ptr(self._buf),
+                ptr(self.x_b), ptr(self.y_b), ptr(self.u_b), ptr(self.v_b),
+                ptr(self.x_s), ptr(self.y_s), ptr(self.u_s), ptr(self.v_s), ptr(self.p_s), self.supervision_enabled,
+                float(self.alpha_evm), float(self.alpha_b), float(self.alpha_e), float(self.alpha_s), float(self.coord_scale), float(self.Re),
+                trainable, self.store_residuals, self._n_f_global, getattr(self, "_n_b_global", 0), self._n_s_global, self._n_ps_global,
+                bool(self.ddp_compat), self.world_size if self.is_distributed else 1,
                 ptr(self.net.flat_params()), ptr(self.net_1.flat_params()) if self.net_1 is not None else 0)
 
     def _fused_step_replayable(self):
@@ -656,8 +683,13 @@ class SolverBase:
 
     def load_checkpoint(self, path):
         """Restore ``save_checkpoint`` state into this solver (same network shapes; the point sets are set by the caller as
-        usual, BEFORE this call, so that the saved lag state replaces the one ``set_eq_training_data`` initialises)."""
-        ck = torch.load(path, map_location=self.device, weights_only=False)
+        usual, BEFORE this call, so that the saved lag state replaces the one ``set_eq_training_data`` initialises).
+
+        The restored Adam moments survive only when training continues WITHOUT the stage-start reset: the reference's
+        ``solve_Adam`` creates a fresh optimizer at epoch 0 of every call (ev :452, ``freeze_evm_net(0)``), so pass
+        ``start_epoch=k`` (the epoch the checkpoint was written at) to ``solve_Adam`` / ``train`` to continue the stage
+        bit-exactly; a plain ``train()`` after ``load_checkpoint`` restarts Adam like the reference does."""
+        ck = torch.load(path, map_location=self.device, weights_only=True)     # tensors, primitives and an optimizer state_dict only
         if ck.get("format") != "nsfnet_b200.checkpoint.v1":
             raise ValueError(f"{path} is not a nsfnet_b200 checkpoint")
         self.net.load_state_dict(ck["net"])
