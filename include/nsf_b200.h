@@ -105,14 +105,12 @@ const char* nsf_last_error(void);
 int nsf_create(int device, const NsfNetDesc* main_net, const NsfNetDesc* evm_or_null, NsfCtx** out);
 int nsf_destroy(NsfCtx* ctx);
 
-/* Select the kernel family of the hidden-layer contractions: 0 = auto (tcgen05 tile-major when the shape is covered, else
- * FFMA), 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 tile-major kernel (default for hidden = 80), 3 = tcgen05 3xTF32
- * layer-major kernel (weights in tensor memory, per-tile state through L2), 4 = tcgen05 3xTF32 tile-major kernel with the
- * stage weights in tensor memory (experimental); 2 / 3 / 4 return NSF_E_SHAPE if the shape is not covered. */
+/* Select the kernel family of the hidden-layer contractions: 0 = auto (the tcgen05 kernel that covers the shape, else FFMA),
+ * 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 kernel with the neurons on the MMA's M (round 1; hidden = 80, 2..6
+ * hidden layers), 3 = tcgen05 3xTF32 kernel with the points on M (hidden = 80 with 2..6 hidden layers: the ev-NSFnet main net;
+ * hidden = 120 with 2..4: NSFnet); 2 / 3 return NSF_E_SHAPE if the shape is not covered. */
 int nsf_set_path(NsfCtx* ctx, int path);
-/* Tuning knob of the layer-major kernel: 12-point tiles per super-batch (1..8, 0 = default 4). */
-int nsf_set_tiles_per_batch(NsfCtx* ctx, int nt);
-/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 2, 3, 4 tcgen05),
+/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 2, 3 tcgen05),
  * [2]=kernel launches issued by the last nsf_* call, [3]=workspace bytes. */
 int nsf_get_info(NsfCtx* ctx, int64_t info[4]);
 
@@ -124,7 +122,7 @@ int nsf_last_kernel_ms(NsfCtx* ctx, float* ms);
 
 /* Diagnostics of the tcgen05 kernel: out == NULL switches per-warp cycle counters on for the following launches;
  * out != NULL (double[256]) synchronises the device and returns the counters of the last launch averaged over CTAs
- * (layout documented at nsf_umma_stage_cycles in csrc/nsf_umma_jet.cu).  Adds clock reads to the kernel: not for
+ * (layout documented at nsf_pm_stage_cycles in csrc/nsf_pm_jet.cu resp. nsf_umma_stage_cycles in csrc/nsf_umma_jet.cu).  Adds clock reads to the kernel: not for
  * timed runs. */
 int nsf_get_stage_cycles(NsfCtx* ctx, double* out);
 

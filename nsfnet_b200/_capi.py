@@ -21,7 +21,7 @@ NSF_MAX_BLOCKS = 2
 NSF_LOSS_SLOTS = 16
 
 EXPORTS = ["nsf_abi_version", "nsf_last_error", "nsf_create", "nsf_destroy", "nsf_set_path", "nsf_get_info",
-           "nsf_set_timing", "nsf_last_kernel_ms", "nsf_get_stage_cycles", "nsf_set_tiles_per_batch",
+           "nsf_set_timing", "nsf_last_kernel_ms", "nsf_get_stage_cycles",
            "nsf_step", "nsf_residuals", "nsf_forward", "nsf_adam", "nsf_selftest_umma",
            "nsf_adam_dev", "nsf_adam_tick", "nsf_lhs_points", "nsf_wall_distance", "nsf_sdf_weights"]
 
@@ -66,8 +66,6 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nsf_destroy.argtypes = [vp]
     lib.nsf_set_path.restype = C.c_int
     lib.nsf_set_path.argtypes = [vp, C.c_int]
-    lib.nsf_set_tiles_per_batch.restype = C.c_int
-    lib.nsf_set_tiles_per_batch.argtypes = [vp, C.c_int]
     lib.nsf_get_info.restype = C.c_int
     lib.nsf_get_info.argtypes = [vp, C.POINTER(i64 * 4)]
     lib.nsf_set_timing.restype = C.c_int
@@ -154,9 +152,6 @@ class Context:
 
     def set_path(self, path: int):
         check(self.lib, self.lib.nsf_set_path(self.h, path))
-
-    def set_tiles_per_batch(self, nt: int):
-        check(self.lib, self.lib.nsf_set_tiles_per_batch(self.h, nt))
 
     def info(self):
         arr = (C.c_int64 * 4)()

@@ -107,8 +107,7 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   nsf_rt_free(ctx->e_buf); nsf_rt_free(ctx->ebar_buf);
 #ifndef NSF_EMU
   nsf_umma_free(ctx);
-  nsf_umma2_free(ctx);
-  nsf_umma3_free(ctx);
+  nsf_pm_free(ctx);
   if (ctx->side) cudaStreamDestroy((cudaStream_t)ctx->side);
   if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
@@ -119,35 +118,34 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   return NSF_OK;
 }
 
-// kernel family the next collocation launch uses: 1 = FFMA, 2 = tcgen05 tile-major, 3 = tcgen05 layer-major
+// kernel family the next collocation launch uses: 1 = FFMA, 2 = tcgen05 with the neurons on M (round 1, hidden = 80 only),
+// 3 = tcgen05 with the points on M (hidden = 80 and hidden = 120).  Auto (0) prefers 3, then 2, then 1.
 static int effective_path(const NsfCtx* ctx) {
 #ifdef NSF_EMU
   return 1;
 #else
   if (ctx->path == 1) return 1;
-  if (!nsf_umma_supported(ctx->main.g)) return 1;
-  if (ctx->path == 4) return 4;
-  return ctx->path == 3 ? 3 : 2;
+  if (ctx->path == 2) return nsf_umma_supported(ctx->main.g) ? 2 : 1;
+  if (nsf_pm_supported(ctx->main.g)) return 3;
+  return nsf_umma_supported(ctx->main.g) ? 2 : 1;
 #endif
 }
 
 extern "C" int nsf_set_path(NsfCtx* ctx, int path) {
-  if (!ctx || path < 0 || path > 4) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
+  if (!ctx || path < 0 || path > 3) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
 #ifdef NSF_EMU
   if (path >= 2) { nsf_set_error("tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE; }
 #else
-  if (path >= 2 && !nsf_umma_supported(ctx->main.g)) {
-    nsf_set_error("tcgen05 path covers hidden = 80 with 2..6 hidden layers; this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
+  if (path == 2 && !nsf_umma_supported(ctx->main.g)) {
+    nsf_set_error("tcgen05 path 2 covers hidden = 80 with 2..6 hidden layers; this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
+    return NSF_E_SHAPE;
+  }
+  if (path == 3 && !nsf_pm_supported(ctx->main.g)) {
+    nsf_set_error("tcgen05 path 3 covers hidden = 80 (2..6 hidden layers) and hidden = 120 (2..4); this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
     return NSF_E_SHAPE;
   }
 #endif
   ctx->path = path;
-  return NSF_OK;
-}
-
-extern "C" int nsf_set_tiles_per_batch(NsfCtx* ctx, int nt) {
-  if (!ctx || nt < 0 || nt > 8) { nsf_set_error("nsf_set_tiles_per_batch: nt must be 0 (default) .. 8"); return NSF_E_ARG; }
-  ctx->umma2_nt = nt;
   return NSF_OK;
 }
 
@@ -162,9 +160,9 @@ extern "C" int nsf_get_stage_cycles(NsfCtx* ctx, double* out) {
 #ifdef NSF_EMU
   (void)out; nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE;
 #else
-  if (!nsf_umma_supported(ctx->main.g)) { nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not cover this net"); return NSF_E_SHAPE; }
-  if (effective_path(ctx) == 4) return nsf_umma3_stage_cycles(ctx, out);
-  return effective_path(ctx) == 3 ? nsf_umma2_stage_cycles(ctx, out) : nsf_umma_stage_cycles(ctx, out);
+  if (effective_path(ctx) == 3) return nsf_pm_stage_cycles(ctx, out);
+  if (effective_path(ctx) == 2) return nsf_umma_stage_cycles(ctx, out);
+  nsf_set_error("nsf_get_stage_cycles: the tcgen05 paths do not cover this net"); return NSF_E_SHAPE;
 #endif
 }
 
@@ -176,12 +174,8 @@ static int launch_jet(NsfCtx* ctx, NsfKernelArgs& a, const float* flat_main, int
     return nsf_umma_launch(ctx, a, flat_main, grid, st, &ctx->launches);
   }
   if (effective_path(ctx) == 3) {
-    NSF_TRY(nsf_umma2_init(ctx));
-    return nsf_umma2_launch(ctx, a, flat_main, grid, st, &ctx->launches);
-  }
-  if (effective_path(ctx) == 4) {
-    NSF_TRY(nsf_umma3_init(ctx));
-    return nsf_umma3_launch(ctx, a, flat_main, grid, st, &ctx->launches);
+    NSF_TRY(nsf_pm_init(ctx));
+    return nsf_pm_launch(ctx, a, flat_main, grid, st, &ctx->launches);
   }
 #endif
   (void)flat_main;
@@ -357,19 +351,14 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   int grids[1 + NSF_MAX_BLOCKS];
   grids[0] = n_f > 0 ? grid_for(ctx, M, 4, n_f) : 0;
 #ifndef NSF_EMU
-  if (n_f > 0 && effective_path(ctx) == 4) {
-    NSF_TRY(nsf_umma3_init(ctx));
-    const long long groups = (n_f + nsf_umma3_group_points() - 1) / nsf_umma3_group_points();
-    grids[0] = (int)(groups < ctx->sms ? groups : ctx->sms);
+  if (n_f > 0 && effective_path(ctx) == 3) {   // one persistent CTA per SM, one tile of 32 / 16 points per iteration
+    NSF_TRY(nsf_pm_init(ctx));
+    grids[0] = nsf_pm_grid(ctx, n_f);
   }
   if (n_f > 0 && effective_path(ctx) == 2) {   // one persistent CTA per SM, a pair of 8-point tiles per iteration
     NSF_TRY(nsf_umma_init(ctx));
     const long long groups = (n_f + nsf_umma_group_points() - 1) / nsf_umma_group_points();
     grids[0] = (int)(groups < ctx->sms ? groups : ctx->sms);
-  }
-  if (n_f > 0 && effective_path(ctx) == 3) {
-    NSF_TRY(nsf_umma2_init(ctx));
-    grids[0] = nsf_umma2_grid(ctx, n_f, ctx->umma2_nt > 0 ? ctx->umma2_nt : 4);
   }
 #endif
   for (int b = 0; b < n_blocks; ++b) grids[1 + b] = blocks[b].n > 0 ? grid_for(ctx, M, 1, blocks[b].n) : 0;
@@ -383,7 +372,7 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   }
   bool side = false;
 #ifndef NSF_EMU
-  side = n_f > 0 && (effective_path(ctx) == 2 || effective_path(ctx) == 4) && blk_rows > 0 && grids[0] + blk_rows <= M.rows;
+  side = n_f > 0 && effective_path(ctx) >= 2 && blk_rows > 0 && grids[0] + blk_rows <= M.rows;
   if (side && !ctx->side) {
     cudaStream_t s2; cudaEvent_t e0, e1;
     NSF_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));

@@ -60,10 +60,8 @@ struct NsfCtx {
   float* e_buf = nullptr;     // [cap] EVM output at the collocation points
   float* ebar_buf = nullptr;  // [cap] d(loss)/d(e)
   long long cap = 0;
-  void* umma = nullptr;  // tcgen05 path state, tile-major kernel (nsf_umma_jet.cu)
-  void* umma2 = nullptr; // tcgen05 path state, layer-major kernel (nsf_umma_jet2.cu)
-  void* umma3 = nullptr; // tcgen05 path state, tile-major kernel with the weights in tensor memory (nsf_umma_jet3.cu)
-  int umma2_nt = 0;      // tiles per super-batch of the layer-major kernel (0 = default)
+  void* umma = nullptr;  // tcgen05 path state, round-1 kernel: neurons on M, 8-point tiles (nsf_umma_jet.cu)
+  void* pm = nullptr;    // tcgen05 path state, points-on-M kernel (nsf_pm_jet.cu)
   void* side = nullptr;     // side stream: the data blocks (boundary / supervised MSE) run beside the EVM forward + jet kernel
   void* ev_fork = nullptr;
   void* ev_join = nullptr;
@@ -100,17 +98,16 @@ int nsf_umma_group_points();
 int nsf_umma_init(NsfCtx* ctx);
 void nsf_umma_free(NsfCtx* ctx);
 int nsf_umma_stage_cycles(NsfCtx* ctx, double* out);
-int nsf_umma2_init(NsfCtx* ctx);
-void nsf_umma2_free(NsfCtx* ctx);
-int nsf_umma2_stage_cycles(NsfCtx* ctx, double* out);
-int nsf_umma2_grid(const NsfCtx* ctx, long long n, int nt);
-int nsf_umma2_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
-int nsf_umma3_group_points();
-int nsf_umma3_init(NsfCtx* ctx);
-void nsf_umma3_free(NsfCtx* ctx);
-int nsf_umma3_stage_cycles(NsfCtx* ctx, double* out);
-int nsf_umma3_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
+
+// nsf_pm_jet.cu (CUDA build only): points-on-M tcgen05 kernel, hidden = 80 and hidden = 120 ------------------------
+int nsf_pm_supported(const NsfNetGeom& g);
+int nsf_pm_tile_points(const NsfNetGeom& g);
+int nsf_pm_init(NsfCtx* ctx);
+void nsf_pm_free(NsfCtx* ctx);
+int nsf_pm_grid(NsfCtx* ctx, long long n);
+int nsf_pm_stage_cycles(NsfCtx* ctx, double* out);
+int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 
 // flat parameter i of the packed image (host + device)
 NSF_HD float nsf_pack_value(const NsfNetGeom& g, const float* flat, int i) {

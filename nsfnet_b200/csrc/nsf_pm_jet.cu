@@ -1,0 +1,813 @@
+// tcgen05 jet kernel, "points on M": the collocation step (jet forward + residuals + reverse pass) of a 2 -> H x L -> 3 tanh
+// MLP with every hidden-layer contraction on the 5th-generation tensor cores, 3xTF32 split for fp32 fidelity.
+//   hidden = 80  (ev-NSFnet main net, L <= 6):  tiles of 32 points, MMA M = 128
+//   hidden = 120 (NSFnet, L <= 4)            :  tiles of 16 points, MMA M = 64
+//
+// Orientation (round 2; the round-1 kernel had the neurons on M and 8 points x 4 streams on N = 32, which left every MMA
+// bound by the re-fetch of its 4 KB weight operand: 43 cycles for 16 cycles of math):
+//   MMA row   m = 4 * point + stream      (streams value, d/dx, d/dy, laplacian; M = 128 rows = 32 points)
+//   MMA col   n = output neuron           (N = H)
+//   forward / dgrad :  D[m, n] = sum_k A[m, k] * Wt[n, k]      A = activations / adjoints of the tile, B = the layer's weights
+//   weight gradient :  dW_l[j, k] += sum_m Zbar[m, j] * Act[m, k]   (contraction over the tile's rows, accumulators resident in
+//                                                                   tensor memory for the whole kernel, flushed every FLUSH tiles)
+// One MMA now carries 32 points for 62 cycles (measured, scripts/probe_pm.cu) instead of 8 points for 43.
+//
+// Operand images of a tile (shared memory):  P (activations a_l going forward, adjoints zbar_l going back) and Q (a_{l-1}, the
+// second operand of the weight gradient), each [hi | lo], rows of 128 bytes = 32 tile rows of ONE neuron, atoms of 4 neurons,
+// 32-byte chunks XOR-swizzled by (neuron & 3): tcgen05 descriptor layout type 1.  The same bytes are read MN-major as the A
+// operand of forward / dgrad and K-major as both operands of the weight gradient (round-1 finding, re-checked by the probes).
+// A thread stores the 4 streams of a (point, neuron) with ONE st.shared.v4.
+// Weights: per MMA stage [hi | lo] x NG blocks of 5 k-steps, K-major, streamed from L2 by TMA bulk copies (measured: > 50 B/clk/SM
+// with every SM streaming) into NG "hi" slots (resident for the stage: read by the correction pass and by the main pass) and
+// two rotating "lo" slots.
+//
+// Warps: 4*NSUB epilogue warps (a warp may only touch TMEM lanes of quadrant warp & 3: 32 rows = 8 points x 4 streams), one
+// issuer warp (tcgen05.mma / commit, one elected lane), one weight producer (one lane).  One tile is in flight per CTA:
+//   stage 0        : layer 0 (K = 2) on FFMA                                        -> P
+//   stage 1..L-1   : hidden layer forward, MMA -> D, epilogue: tanh jet             -> P (in place), stash (t, zx, zy, z_lap) to L2
+//   stage L        : output layer (N = 16), residuals, loss sums, adjoint seeds, output-layer dgrad / wgrad on FFMA -> P, Q
+//   stage L+1..2L-1: layer l = 2L - s: dgrad MMA -> D, weight-gradient MMAs; epilogue: adjoint through tanh -> P, Q
+// The epilogue thread reads its TMEM lane (= row = point, stream) for 4 neurons and a 4x4 shuffle transpose inside the quad of
+// lanes hands every lane the 4 streams of ONE (point, neuron).  In the reverse stages the epilogue computes zbar while the
+// weight-gradient MMAs still read P and Q, parks it in the (free) D columns of tensor memory, and stores it once the
+// weight-gradient MMAs of ITS rows have completed (wdone[row group]).
+#include "nsf_internal.h"
+#include "nsf_tc.cuh"
+#include "nsf_jet_math.cuh"
+#include <cstdlib>
+
+using namespace nsftc;
+
+namespace {
+
+constexpr int FLUSH = 16;   // tiles between flushes of the TMEM weight-gradient accumulators (bounds the truncating accumulations)
+
+template <int H_, int MT_>
+struct Cfg {
+  static constexpr int H = H_, MT = MT_;
+  static constexpr int PTS = MT / 4;             // points per tile
+  static constexpr int NQ = MT / 32;             // 32-row groups of an operand image
+  static constexpr int KS = H / 8;               // k-steps of a layer contraction
+  static constexpr int GK = 5;                   // k-steps per weight block
+  static constexpr int NG = KS / GK;             // weight blocks per part (hi / lo) and stage
+  static constexpr int NB = H;                   // N of the forward / dgrad MMAs
+  static constexpr int DWN = ((H + 15) / 16) * 16;  // N of the weight-gradient MMAs (M = 128 needs N % 16 == 0)
+  static constexpr int NSUB = MT == 128 ? 4 : 3; // epilogue warps per TMEM quadrant
+  static constexpr int NEW = 4 * NSUB;           // epilogue warps
+  static constexpr int NWORK = MT == 128 ? NSUB : 2 * NSUB;  // workers (warps resp. half-warps) per quadrant
+  static constexpr int NPW = H / NWORK;          // neurons per worker
+  static constexpr int NCH = NPW / 4;            // 4-neuron chunks per worker
+  static constexpr int NEPI = NEW * 32;
+  static constexpr int NTHREADS = (NEW + 2) * 32;
+  static constexpr uint32_t GRP = (H / 4) * 512; // one 32-row group of one image part
+  static constexpr uint32_t PART = NQ * GRP;     // hi or lo
+  static constexpr uint32_t IMG = 2 * PART;
+  static constexpr uint32_t WSUB = NB * 32;      // one k-step of one weight part
+  static constexpr uint32_t WBLK = GK * WSUB;
+  static constexpr uint32_t WSUB_O = 16 * 32;    // output layer: 16 rows (3 real)
+  static constexpr uint32_t WBLK_O = GK * WSUB_O;
+  static constexpr uint32_t WSTAGE = 2 * NG * WBLK;   // one stage image in global memory: [hi blocks | lo blocks]
+  static constexpr uint32_t OFF_P = 0, OFF_Q = IMG, OFF_WHI = 2 * IMG, OFF_WLO = OFF_WHI + NG * WBLK, OFF_MISC = OFF_WLO + 2 * WBLK;
+  static constexpr bool GWL_SMEM = MT == 128;   // 18 warps leave 96 registers per thread: the output-layer gradient goes to shared memory
+  static constexpr uint32_t MISC = MT == 128 ? 15360 : 12288;
+  static constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;
+  static_assert(H % 8 == 0 && KS % GK == 0 && H % NWORK == 0 && NPW % 4 == 0, "shape");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+  static_assert(OFF_Q % 1024 == 0 && OFF_WHI % 1024 == 0 && PART % 1024 == 0, "swizzle phase");
+};
+
+struct PArgs {
+  NsfNetGeom g;
+  const float* pk;       // FFMA packed image: layer 0, biases, output layer rows
+  const uint8_t* wimg;   // (2L-1) stage images: WF_1..WF_{L-1}, W_out, WB_{L-1}..WB_1
+  const float* x; const float* y; long long n;
+  const float* e_in; const float* vtm_in; float* vtm_out; const float* w;
+  float inv_Re, vis_t0, alpha_evm, cs1, cs2, k4, c_eq;
+  int has_evm;
+  float* resid_out; float* vis_t_out; float* ebar_out;
+  float* stash;          // [grid][L][PTS][H] float4
+  float* scratch;        // gradient rows [grid][gs_row]
+  int n_tiles;
+  long long* dbg;        // optional [grid][32] cycle counters
+};
+
+template <int H, int L, int NGWL>
+struct Misc {
+  uint64_t ready;        // operands of the next MMA stage written, previous results consumed (one arrival per epilogue warp)
+  uint64_t dfull;        // forward / dgrad MMAs of the stage complete
+  uint64_t wdone[4];     // weight-gradient MMAs over row group q complete (P / Q rows of the group may be rewritten)
+  uint64_t hi_full[3], hi_free[3], lo_full[2], lo_free[2];
+  uint32_t tmem_base, pad;
+  float loss[4][12];     // per TMEM quadrant: w eq1^2, w eq2^2, w eq3^2, w eq4^2, vis_t, count, gbL[0..2]
+  float gb[4][L][H];     // bias gradients, one private copy per quadrant (single owner lane per entry: deterministic)
+  float gw0x[4][H], gw0y[4][H];
+  float gwl[NGWL ? NGWL : 1][3][NGWL ? H : 1];   // output-layer weight gradient per quadrant (NGWL = 4), or kept in registers (NGWL = 0)
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t layout_type) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29); }
+__host__ __device__ constexpr uint32_t lbo_field(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
+
+// TMEM <-> registers: this thread's lane (row), 4 consecutive columns.  MT = 128: the warp's 32 lanes.  MT = 64: the tile's rows
+// sit in lanes 0..15 of every quadrant; the two half-warps address the same 16 lanes at columns c and c + HALF.
+template <int MT, int HALF>
+__device__ __forceinline__ void ld_d4(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  if (MT == 128) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+  else asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr), "n"(HALF));
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+template <int MT, int HALF>
+__device__ __forceinline__ void st_d4(uint32_t taddr, const float* v) {
+  if (MT == 128) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
+  else asm volatile("tcgen05.st.sync.aligned.16x32bx2.x4.b32 [%0], %5, {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "n"(HALF) : "memory");
+}
+
+// lane s of a quad holds v[i] = (stream s, neuron i); afterwards lane i holds w[s] = (stream s, neuron i)   (scripts/probe_pm.cu)
+__device__ __forceinline__ void quad_transpose(const float v[4], float w[4], int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+  const float sa = b0 ? v[0] : v[1], sb = b0 ? v[2] : v[3];
+  const float ra = __shfl_xor_sync(0xffffffffu, sa, 1), rb = __shfl_xor_sync(0xffffffffu, sb, 1);
+  const float p0 = b0 ? ra : v[0], p1 = b0 ? v[1] : ra;
+  const float q0 = b0 ? rb : v[2], q1 = b0 ? v[3] : rb;
+  const float s0 = b1 ? p0 : q0, s1 = b1 ? p1 : q1;
+  const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float k0 = b1 ? q0 : p0, k1 = b1 ? q1 : p1;
+  w[0] = b1 ? r0 : k0; w[1] = b1 ? r1 : k1; w[2] = b1 ? k0 : r0; w[3] = b1 ? k1 : r1;
+}
+
+// the 4 streams of one (point, neuron) -> [hi | lo] image at shared address `addr` (hi; lo is PART bytes further)
+template <uint32_t PART>
+__device__ __forceinline__ void store_jet(uint32_t addr, const float v[4]) {
+  float hi[4], lo[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) split_tf32_fast(v[s], hi[s], lo[s]);
+  sts4(addr, hi[0], hi[1], hi[2], hi[3]);
+  sts4(addr + PART, lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int H, int L, int MT, bool TRAIN>
+__global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(const PArgs a) {
+  using C = Cfg<H, MT>;
+  using MiscT = Misc<H, L, C::GWL_SMEM ? 4 : 0>;
+  static_assert(sizeof(MiscT) <= C::MISC, "misc region too small");
+  static_assert((L - 1) * C::DWN + C::NB <= 512, "tensor memory columns");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  MiscT* misc = reinterpret_cast<MiscT*>(smem + C::OFF_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const NsfNetGeom& g = a.g;
+  constexpr int NMS = TRAIN ? 2 * L - 1 : L;          // MMA stages per tile
+  constexpr uint32_t DCOL = (L - 1) * C::DWN;         // D (forward / dgrad results) behind the weight-gradient accumulators
+  const uint32_t smem_base = smem_u32(smem);
+  const bool dbg = a.dbg != nullptr;
+
+  if (warp == C::NEW) tmem_alloc(&misc->tmem_base, 512);
+  if (tid == 0) {
+    if (smem_base & 1023u) __trap();
+    mbar_init(&misc->ready, C::NEW); mbar_init(&misc->dfull, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&misc->wdone[i], 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&misc->hi_full[i], 1); mbar_init(&misc->hi_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&misc->lo_full[i], 1); mbar_init(&misc->lo_free[i], 1); }
+    mbar_fence_init();
+  }
+  {
+    float* acc = &misc->loss[0][0];
+    constexpr int NACC = (int)((sizeof(MiscT) - offsetof(MiscT, loss)) / 4);
+    for (int i = tid; i < NACC; i += C::NTHREADS) acc[i] = 0.f;
+  }
+  // the weight-gradient MMAs (M = 128) read image rows past the H real neurons: keep them finite
+  for (uint32_t i = tid * 16; i < 2 * C::IMG; i += C::NTHREADS * 16) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc->tmem_base;
+  const int my_tiles = ((int)blockIdx.x < a.n_tiles) ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == C::NEW) {
+    // =========================== issuer warp ===========================
+    const uint32_t leader = elect_one();
+    const uint32_t sb4 = smem_base >> 4;
+    uint32_t ready_ph = 0, stage_ctr = 0, lo_ctr0 = 0, lo_ctr1 = 0;
+    long long c_wait = 0, c_issue = 0, c_wwait = 0;
+    constexpr uint32_t AHI = desc_hi_t(512, 1), BHI = desc_hi(256);
+    for (int t = 0; t < my_tiles; ++t) {
+      const bool zero_dw = (t % FLUSH) == 0;
+#pragma unroll 1
+      for (int ms = 0; ms < NMS; ++ms) {
+        const int s = ms + 1;
+        const bool outst = (s == L);
+        const uint32_t wsub = outst ? C::WSUB_O : C::WSUB;
+        const uint32_t idesc = idesc_tf32(MT, outst ? 16 : C::NB, 1, 0);
+        const uint32_t d_col = tmem + DCOL;
+        long long t0 = 0, t1 = 0;
+        if (dbg) t0 = clock64();
+        mbar_wait(&misc->ready, ready_ph); ready_ph ^= 1u;
+        tc_fence_after();
+        if (dbg) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
+        const uint32_t a_hi = sb4 + (C::OFF_P >> 4) + lbo_field(C::GRP), a_lo = a_hi + (C::PART >> 4);
+        // correction products first (the tensor core truncates when it adds into the accumulator: small terms while it is small)
+#pragma unroll
+        for (int gi = 0; gi < C::NG; ++gi) {
+          if (dbg) t1 = clock64();
+          mbar_wait(&misc->hi_full[gi], stage_ctr & 1u);
+          if ((gi & 1) == 0) { mbar_wait(&misc->lo_full[0], lo_ctr0 & 1u); ++lo_ctr0; }
+          else { mbar_wait(&misc->lo_full[1], lo_ctr1 & 1u); ++lo_ctr1; }
+          if (dbg) c_wwait += clock64() - t1;
+          const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
+          const uint32_t w_lo = sb4 + ((C::OFF_WLO + (gi & 1) * C::WBLK) >> 4) + lbo_field(128);
+#pragma unroll
+          for (int kk = 0; kk < C::GK; ++kk) {
+            const uint32_t da = (uint32_t)((gi * C::GK + kk) * 1024) >> 4, dw = (kk * wsub) >> 4;
+            mma_tf32_elect2(d_col, a_lo + da, AHI, w_hi + dw, BHI, idesc, (gi | kk) > 0, leader);
+            mma_tf32_elect2(d_col, a_hi + da, AHI, w_lo + dw, BHI, idesc, 1, leader);
+          }
+          mma_commit_elect(&misc->lo_free[gi & 1], leader);
+        }
+#pragma unroll
+        for (int gi = 0; gi < C::NG; ++gi) {
+          const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
+#pragma unroll
+          for (int kk = 0; kk < C::GK; ++kk) {
+            const uint32_t da = (uint32_t)((gi * C::GK + kk) * 1024) >> 4, dw = (kk * wsub) >> 4;
+            mma_tf32_elect2(d_col, a_hi + da, AHI, w_hi + dw, BHI, idesc, 1, leader);
+          }
+          mma_commit_elect(&misc->hi_free[gi], leader);
+        }
+        mma_commit_elect(&misc->dfull, leader);
+        ++stage_ctr;
+        if (TRAIN && s > L) {
+          // weight gradient of layer l = 2L - s: dW_l[128, DWN] += P[rows, j]^T Q[rows, k], both images read K-major (type 1)
+          const int l = 2 * L - s;
+          const uint32_t dw_col = tmem + (uint32_t)((l - 1) * C::DWN);
+          const uint32_t wdesc = idesc_tf32(128, C::DWN, 0, 0);
+          const uint32_t p_hi = sb4 + (C::OFF_P >> 4), p_lo = p_hi + (C::PART >> 4);
+          const uint32_t q_hi = sb4 + (C::OFF_Q >> 4), q_lo = q_hi + (C::PART >> 4);
+#pragma unroll
+          for (int qq = 0; qq < C::NQ; ++qq) {
+#pragma unroll
+            for (int kr = 0; kr < 4; ++kr) {
+              const uint32_t o = (uint32_t)(qq * C::GRP + kr * 32) >> 4;
+              mma_tf32_elect2(dw_col, p_lo + o, AHI, q_hi + o, AHI, wdesc, !(zero_dw && qq == 0 && kr == 0), leader);
+              mma_tf32_elect2(dw_col, p_hi + o, AHI, q_lo + o, AHI, wdesc, 1, leader);
+              mma_tf32_elect2(dw_col, p_hi + o, AHI, q_hi + o, AHI, wdesc, 1, leader);
+            }
+            mma_commit_elect(&misc->wdone[qq], leader);
+          }
+        }
+        __syncwarp();
+        if (dbg) c_issue += clock64() - t0;
+      }
+    }
+    if (dbg && lane == 0) {
+      long long* d = a.dbg + (size_t)blockIdx.x * 32;
+      d[0] = c_wait; d[1] = c_issue; d[2] = c_wwait; d[3] = (long long)my_tiles * NMS;
+    }
+  } else if (warp == C::NEW + 1) {
+    // =========================== weight producer (one lane) ===========================
+    if (lane == 0) {
+      const long long total = (long long)my_tiles * NMS;
+      uint32_t lo_use0 = 0, lo_use1 = 0;
+      int img = 0;
+      for (long long n = 0; n < total; ++n) {
+        const uint8_t* src = a.wimg + (size_t)img * C::WSTAGE;
+        const uint32_t blk = (img == L - 1) ? C::WBLK_O : C::WBLK;
+#pragma unroll
+        for (int gi = 0; gi < C::NG; ++gi) {
+          if (n >= 1) mbar_wait(&misc->hi_free[gi], (uint32_t)((n - 1) & 1));
+          mbar_expect_tx(&misc->hi_full[gi], blk);
+          tma_bulk_g2s(smem + C::OFF_WHI + gi * C::WBLK, src + (size_t)gi * C::WBLK, blk, &misc->hi_full[gi]);
+          if ((gi & 1) == 0) {
+            if (lo_use0 >= 1) mbar_wait(&misc->lo_free[0], (lo_use0 - 1) & 1u);
+            ++lo_use0;
+            mbar_expect_tx(&misc->lo_full[0], blk);
+            tma_bulk_g2s(smem + C::OFF_WLO, src + (size_t)(C::NG + gi) * C::WBLK, blk, &misc->lo_full[0]);
+          } else {
+            if (lo_use1 >= 1) mbar_wait(&misc->lo_free[1], (lo_use1 - 1) & 1u);
+            ++lo_use1;
+            mbar_expect_tx(&misc->lo_full[1], blk);
+            tma_bulk_g2s(smem + C::OFF_WLO + C::WBLK, src + (size_t)(C::NG + gi) * C::WBLK, blk, &misc->lo_full[1]);
+          }
+        }
+        if (++img == NMS) img = 0;
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int q = warp & 3, sub = warp >> 2;
+    const int l16 = MT == 128 ? lane : (lane & 15);
+    const int worker = MT == 128 ? sub : 2 * sub + (lane >> 4);
+    const int nb = C::NPW * worker;                       // first neuron of this worker
+    const int kq = lane & 3;                              // neuron within a chunk (after the transpose) == stream before it
+    const int pt_loc = (MT == 128 ? 8 : 4) * q + (l16 >> 2);   // point of the tile this thread works for
+    const int rg = MT == 128 ? q : (q >> 1);              // 32-row group of the images its rows are in
+    const bool primary = worker == 0;                     // one worker per quadrant does the per-point bookkeeping
+    const bool red_lane = l16 < 4;                        // lane that owns the warp-reduced sums of neuron kq
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // TMEM address of this worker's D columns: chunk c at + 4c (MT = 64: the upper half-warp reads NPW columns further)
+    const uint32_t d_thr = tmem + lane_addr + DCOL + (uint32_t)(MT == 128 ? nb : C::NPW * 2 * sub);
+    // byte offset of this thread's float4 (neuron nb + kq, chunk 0) inside an image part; chunk c: + 512 c
+    const uint32_t img_thr = (uint32_t)(pt_loc >> 3) * C::GRP + (uint32_t)(nb >> 2) * 512u + (uint32_t)kq * 128u +
+                             (uint32_t)((((pt_loc >> 1) & 3) ^ kq) * 32) + (uint32_t)(pt_loc & 1) * 16u;
+    const uint32_t p_thr = smem_base + C::OFF_P + img_thr, q_thr = smem_base + C::OFF_Q + img_thr;
+    const int k0 = nb + kq;                               // this thread's neuron in chunk 0 (chunk c: + 4c)
+    const float* pk = a.pk;
+    float4* stash_thr = TRAIN ? reinterpret_cast<float4*>(a.stash) + ((size_t)blockIdx.x * L * C::PTS + pt_loc) * H + k0 : nullptr;
+    constexpr size_t STL = (size_t)C::PTS * H;            // stash stride between layers (float4)
+    float gwl[3][C::NCH];
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+#pragma unroll
+      for (int c = 0; c < C::NCH; ++c) gwl[o][c] = 0.f;
+    uint32_t dfull_ph = 0, rs_ctr = 0;
+    long long c_dwait = 0, c_wwait = 0, c_work = 0;
+
+    auto red_pts = [&](float v) {      // sum over the points of this worker's rows (fixed tree: deterministic)
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      if (MT == 128) v += __shfl_xor_sync(0xffffffffu, v, 16);
+      return v;
+    };
+    auto hand_over = [&]() {           // operands visible to the async proxy, TMEM accesses retired -> issuer
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&misc->ready);
+    };
+
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long p_tile = ((long long)blockIdx.x + (long long)t * gridDim.x) * C::PTS;
+      const long long gp = p_tile + pt_loc;
+      const bool ok = gp < a.n;
+      const float xv = ok ? __ldg(a.x + gp) : 0.f, yv = ok ? __ldg(a.y + gp) : 0.f;
+      long long t0 = 0, t1 = 0;
+      if (dbg) t0 = clock64();
+      // ---------------- stage 0: layer 0 (K = 2) ----------------
+#pragma unroll
+      for (int c = 0; c < C::NCH; ++c) {
+        const int k = k0 + 4 * c;
+        const float w0x = __ldg(pk + g.pk_w0x() + k), w0y = __ldg(pk + g.pk_w0y() + k), b0 = __ldg(pk + g.pk_b0() + k);
+        const float z[4] = {fmaf(w0x, xv, fmaf(w0y, yv, b0)), w0x, w0y, 0.f};
+        float v[4];
+        nsf_jet_fwd(z, v);
+        store_jet<C::PART>(p_thr + 512u * c, v);
+        if (TRAIN) __stcg(stash_thr + 4 * c, make_float4(v[0], z[1], z[2], z[3]));
+      }
+      hand_over();
+      if (dbg) { t1 = clock64(); c_work += t1 - t0; }
+      // ---------------- stages 1 .. L-1: hidden layers forward ----------------
+#pragma unroll 1
+      for (int s = 1; s < L; ++s) {
+        float bias[C::NCH];
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) bias[c] = __ldg(pk + g.pk_b(s) + k0 + 4 * c);
+        if (dbg) t0 = clock64();
+        mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
+        tc_fence_after();
+        if (dbg) { t1 = clock64(); c_dwait += t1 - t0; }
+        float d[C::NCH][4];
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) ld_d4<MT, C::NPW>(d_thr + 4 * c, d[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) {
+          float z[4], v[4];
+          quad_transpose(d[c], z, lane);
+          z[0] += bias[c];
+          nsf_jet_fwd(z, v);
+          store_jet<C::PART>(p_thr + 512u * c, v);
+          if (TRAIN) __stcg(stash_thr + s * STL + 4 * c, make_float4(v[0], z[1], z[2], z[3]));
+        }
+        hand_over();
+        if (dbg) c_work += clock64() - t1;
+      }
+      // ---------------- stage L: output layer, residuals, adjoint seeds ----------------
+      float ob[4][3];      // adjoint of the outputs: [stream][u, v, p]
+      {
+        float pre_e = 0.f, pre_vtm = a.vis_t0, pre_w = 1.f;
+        if (ok) {
+          if (a.has_evm) { pre_e = __ldg(a.e_in + gp); if (a.vtm_in) pre_vtm = __ldg(a.vtm_in + gp); }
+          if (a.w) pre_w = __ldg(a.w + gp);
+        }
+        const float bo0 = __ldg(pk + g.pk_bl() + 0), bo1 = __ldg(pk + g.pk_bl() + 1), bo2 = __ldg(pk + g.pk_bl() + 2);
+        if (dbg) t0 = clock64();
+        mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
+        tc_fence_after();
+        if (dbg) { t1 = clock64(); c_dwait += t1 - t0; }
+        float o[4];
+        ld_d4<MT, 4>(tmem + lane_addr + DCOL, o);           // this row's (u, v, p, -) of stream kq
+        tmem_ld_wait();
+        if (MT == 64) {                                     // the upper half-warp read the neighbouring columns: take the lower one's
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = __shfl_sync(0xffffffffu, o[i], lane & 15);
+        }
+        if (kq == 0) { o[0] += bo0; o[1] += bo1; o[2] += bo2; }
+        float U[4], V[4], Pp[4];
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) {
+          const int src = (lane & ~3) | ss;
+          U[ss] = __shfl_sync(0xffffffffu, o[0], src); V[ss] = __shfl_sync(0xffffffffu, o[1], src); Pp[ss] = __shfl_sync(0xffffffffu, o[2], src);
+        }
+        const float u = U[0], v = V[0];
+        const float ux = a.cs1 * U[1], vx = a.cs1 * V[1], px = a.cs1 * Pp[1];
+        const float uy = a.cs1 * U[2], vy = a.cs1 * V[2], py = a.cs1 * Pp[2];
+        const float ul = a.cs2 * U[3], vl = a.cs2 * V[3];
+        float ee = 0.f, vis = 0.f;
+        if (a.has_evm) { ee = pre_e; vis = ok ? fminf(a.vis_t0, pre_vtm) : a.vis_t0; }
+        const float nu = a.inv_Re + vis;
+        const float eq1 = (u * ux + v * uy) + px - nu * ul;
+        const float eq2 = (u * vx + v * vy) + py - nu * vl;
+        const float eq3 = ux + vy;
+        const float eq4 = a.has_evm ? (eq1 * (u - 0.5f) + eq2 * (v - 0.5f)) - ee : 0.f;
+        const float cw = (TRAIN && ok) ? a.c_eq * pre_w : 0.f;
+        const float g1 = cw * (2.f * eq1 + a.k4 * eq4 * (u - 0.5f));
+        const float g2 = cw * (2.f * eq2 + a.k4 * eq4 * (v - 0.5f));
+        const float g3 = 2.f * cw * eq3;
+        const float g4 = a.k4 * cw * eq4;
+        ob[0][0] = g1 * ux + g2 * vx + g4 * eq1; ob[0][1] = g1 * uy + g2 * vy + g4 * eq2; ob[0][2] = 0.f;
+        ob[1][0] = a.cs1 * (g1 * u + g3); ob[1][1] = a.cs1 * (g2 * u); ob[1][2] = a.cs1 * g1;
+        ob[2][0] = a.cs1 * (g1 * v); ob[2][1] = a.cs1 * (g2 * v + g3); ob[2][2] = a.cs1 * g2;
+        ob[3][0] = -a.cs2 * nu * g1; ob[3][1] = -a.cs2 * nu * g2; ob[3][2] = 0.f;
+        if (sub == 0) {                                     // warp-uniform: one warp per quadrant does the per-point bookkeeping
+          if (primary && ok) {                              // (MT = 64: its lower half-warp; the upper one works for the same rows)
+            if (a.resid_out) {
+              const float e4[4] = {eq1, eq2, eq3, eq4};
+              float mine = e4[0];
+#pragma unroll
+              for (int i = 1; i < 4; ++i) mine = kq == i ? e4[i] : mine;
+              a.resid_out[(long long)kq * a.n + gp] = mine;
+            }
+            if (kq == 0 && a.vis_t_out) a.vis_t_out[gp] = vis;
+            if (kq == 1 && a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
+            if (TRAIN && kq == 2 && a.ebar_out) a.ebar_out[gp] = -g4;
+          }
+          // loss sums of this quadrant's points (lanes with kq == 0 carry one point each)
+          const bool own = primary && kq == 0, cnt = own && ok;
+          const float r[9] = {cnt ? pre_w * eq1 * eq1 : 0.f, cnt ? pre_w * eq2 * eq2 : 0.f, cnt ? pre_w * eq3 * eq3 : 0.f, cnt ? pre_w * eq4 * eq4 : 0.f,
+                              cnt ? vis : 0.f, cnt ? 1.f : 0.f, own ? ob[0][0] : 0.f, own ? ob[0][1] : 0.f, own ? ob[0][2] : 0.f};
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const float vsum = red_pts(r[i]);
+            if (lane == 0) misc->loss[q][i] += vsum;
+          }
+        }
+        if (!TRAIN) { if (dbg) c_work += clock64() - t1; }
+      }
+      if (TRAIN) {
+        {
+          // output layer backward on FFMA (3 outputs): adjoint of a_{L-1}, weight gradient of the output layer
+          float4 stl[C::NCH];
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) stl[c] = __ldcg(stash_thr + (L - 1) * STL + 4 * c);
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) {
+            const int k = k0 + 4 * c;
+            const float wl0 = __ldg(pk + g.pk_wl() + k), wl1 = __ldg(pk + g.pk_wl() + g.HP + k), wl2 = __ldg(pk + g.pk_wl() + 2 * g.HP + k);
+            float ab[4], act[4], zb[4];
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) ab[ss] = fmaf(ob[ss][0], wl0, fmaf(ob[ss][1], wl1, ob[ss][2] * wl2));
+            nsf_act_from_stash(stl[c], act);
+            float gl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) {
+              gl[0] = fmaf(ob[ss][0], act[ss], gl[0]);
+              gl[1] = fmaf(ob[ss][1], act[ss], gl[1]);
+              gl[2] = fmaf(ob[ss][2], act[ss], gl[2]);
+            }
+            if (C::GWL_SMEM) {
+#pragma unroll
+              for (int o = 0; o < 3; ++o) {
+                const float vsum = red_pts(gl[o]);
+                if (red_lane) misc->gwl[q][o][k] += vsum;
+              }
+            } else {
+#pragma unroll
+              for (int o = 0; o < 3; ++o) gwl[o][c] += gl[o];
+            }
+            nsf_zbar_from(stl[c], ab, zb);
+            store_jet<C::PART>(p_thr + 512u * c, zb);
+            const float sb0 = red_pts(zb[0]);
+            if (red_lane) misc->gb[q][L - 1][k] += sb0;
+          }
+          float4 stm[C::NCH];
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) stm[c] = __ldcg(stash_thr + (L - 2) * STL + 4 * c);
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) {
+            float am[4];
+            nsf_act_from_stash(stm[c], am);
+            store_jet<C::PART>(q_thr + 512u * c, am);
+          }
+          hand_over();
+          if (dbg) c_work += clock64() - t1;
+        }
+        // ---------------- stages L+1 .. 2L-1: reverse of hidden layer l = L-1 .. 1; D = adjoint of a_{l-1} ----------------
+#pragma unroll 1
+        for (int lm1 = L - 2; lm1 >= 0; --lm1) {       // lm1 = l - 1: the layer whose tanh is differentiated in this stage
+          float4 st1[C::NCH];
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + lm1 * STL + 4 * c);
+          if (dbg) t0 = clock64();
+          mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
+          tc_fence_after();
+          if (dbg) { t1 = clock64(); c_dwait += t1 - t0; }
+          float d[C::NCH][4];
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) ld_d4<MT, C::NPW>(d_thr + 4 * c, d[c]);
+          tmem_ld_wait();
+          if (lm1 >= 1) {
+#pragma unroll
+            for (int c = 0; c < C::NCH; ++c) {
+              float ab[4], zb[4];
+              quad_transpose(d[c], ab, lane);
+              nsf_zbar_from(st1[c], ab, zb);
+              const float sb0 = red_pts(zb[0]);
+              if (red_lane) misc->gb[q][lm1][k0 + 4 * c] += sb0;
+              st_d4<MT, C::NPW>(d_thr + 4 * c, zb);     // park zbar_{l-1} in this thread's own (now free) D cells
+            }
+            // a_{l-2} comes from the stash alone; the loads fly while this warp waits for the weight-gradient MMAs
+#pragma unroll
+            for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + (lm1 - 1) * STL + 4 * c);
+            tmem_st_wait();
+            if (dbg) { t0 = clock64(); c_work += t0 - t1; }
+            // the weight-gradient MMAs of this stage still read P and Q: wait for those over this thread's rows
+            mbar_wait(&misc->wdone[rg], rs_ctr & 1u);
+            ++rs_ctr;
+            if (dbg) { t1 = clock64(); c_wwait += t1 - t0; }
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < C::NCH; ++c) ld_d4<MT, C::NPW>(d_thr + 4 * c, d[c]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < C::NCH; ++c) {
+              float am[4];
+              store_jet<C::PART>(p_thr + 512u * c, d[c]);
+              nsf_act_from_stash(st1[c], am);
+              store_jet<C::PART>(q_thr + 512u * c, am);
+            }
+            hand_over();
+            if (dbg) c_work += clock64() - t1;
+          } else {
+            // layer 0: its weight gradient (K = 2) and bias gradient on FFMA; nothing goes back to the tensor core
+#pragma unroll
+            for (int c = 0; c < C::NCH; ++c) {
+              const int k = k0 + 4 * c;
+              float ab[4], zb[4];
+              quad_transpose(d[c], ab, lane);
+              nsf_zbar_from(st1[c], ab, zb);
+              const float sb0 = red_pts(zb[0]);
+              const float sx = red_pts(fmaf(zb[0], xv, zb[1])), sy = red_pts(fmaf(zb[0], yv, zb[2]));
+              if (red_lane) { misc->gb[q][0][k] += sb0; misc->gw0x[q][k] += sx; misc->gw0y[q][k] += sy; }
+            }
+            if (dbg) { t0 = clock64(); c_work += t0 - t1; }
+            // every weight-gradient MMA of the tile: P and Q are rewritten by the next tile's stage 0 / output stage, and the flush follows
+#pragma unroll
+            for (int i = 0; i < C::NQ; ++i) mbar_wait(&misc->wdone[i], rs_ctr & 1u);
+            ++rs_ctr;
+            tc_fence_before();
+            if (dbg) c_wwait += clock64() - t0;
+          }
+        }
+        if ((t + 1) % FLUSH == 0 || t == my_tiles - 1) {
+          // dW_l accumulators (TMEM lane = j, columns (l-1)*DWN + k) -> this CTA's gradient row; every weight-gradient MMA has
+          // completed (all wdone barriers were waited on above), the next one is issued L stages from here
+          tc_fence_after();
+          float* grow = a.scratch + (size_t)blockIdx.x * g.gs_row();
+          const bool first = t < FLUSH;
+          const int j = q * 32 + lane;
+          for (int l = 1 + sub; l < L; l += C::NSUB) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < C::DWN; c0 += 16) {
+              float v[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)((l - 1) * C::DWN + c0), v);
+              tmem_ld_wait();
+              if (j < H) {
+                float* dst = grow + g.gs_w(l) + (size_t)j * g.HP + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  if (c0 + i < H) {
+                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    float4* d4 = reinterpret_cast<float4*>(dst + i);
+                    if (!first) { const float4 p = *d4; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                    *d4 = o;
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+        }
+      }
+    }
+    if (dbg && lane == 0) {
+      long long* d = a.dbg + (size_t)blockIdx.x * 32 + 4;
+      if (warp == 0) { d[0] = c_dwait; d[1] = c_wwait; d[2] = c_work; }
+      if (warp == C::NEW - 1) { d[4] = c_dwait; d[5] = c_wwait; d[6] = c_work; }
+    }
+    // ---- CTA epilogue: per-quadrant accumulators and per-thread partials -> this CTA's gradient row ----
+    if (a.scratch) {
+      float* grow = a.scratch + (size_t)blockIdx.x * g.gs_row();
+      float* gwls = C::GWL_SMEM ? &misc->gwl[0][0][0] : reinterpret_cast<float*>(smem + C::OFF_P);   // [4 quadrants][3][H] (the operand images are free now)
+      if (TRAIN && !C::GWL_SMEM) {
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c)
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            const float vsum = red_pts(gwl[o][c]);
+            if (red_lane) gwls[(q * 3 + o) * H + k0 + 4 * c] = vsum;
+          }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(C::NEPI) : "memory");
+      if (TRAIN) {
+        for (int k = tid; k < H; k += C::NEPI) {
+          grow[g.gs_w0x() + k] = (misc->gw0x[0][k] + misc->gw0x[1][k]) + (misc->gw0x[2][k] + misc->gw0x[3][k]);
+          grow[g.gs_w0y() + k] = (misc->gw0y[0][k] + misc->gw0y[1][k]) + (misc->gw0y[2][k] + misc->gw0y[3][k]);
+#pragma unroll
+          for (int l = 0; l < L; ++l) {
+            const float v = (misc->gb[0][l][k] + misc->gb[1][l][k]) + (misc->gb[2][l][k] + misc->gb[3][l][k]);
+            grow[(l == 0 ? g.gs_b0() : g.gs_b(l)) + k] = v;
+          }
+#pragma unroll
+          for (int o = 0; o < 3; ++o)
+            grow[g.gs_wl() + o * g.HP + k] = (gwls[(0 * 3 + o) * H + k] + gwls[(1 * 3 + o) * H + k]) + (gwls[(2 * 3 + o) * H + k] + gwls[(3 * 3 + o) * H + k]);
+          grow[g.gs_wl() + 3 * g.HP + k] = 0.f;
+        }
+        if (tid < 4) grow[g.gs_bl() + tid] = tid < 3 ? (misc->loss[0][6 + tid] + misc->loss[1][6 + tid]) + (misc->loss[2][6 + tid] + misc->loss[3][6 + tid]) : 0.f;
+      }
+      if (tid < NSF_LOSS_SLOTS) grow[g.gs_loss() + tid] = tid < 6 ? (misc->loss[0][tid] + misc->loss[1][tid]) + (misc->loss[2][tid] + misc->loss[3][tid]) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::NEW) tmem_dealloc(tmem, 512);
+}
+
+// weight stage images: thread per (image, n, k).  Element (n, k) of part p lives at
+//   p * NG * WBLK + (k / 40) * WBLK + ((k % 40) / 8) * (N_img * 32) + (n / 8) * 256 + ((k / 4) & 1) * 128 + (n % 8) * 16 + (k % 4) * 4
+template <int H, int MT>
+__global__ void nsf_pm_pack_kernel(NsfNetGeom g, const float* __restrict__ flat, uint8_t* __restrict__ wimg) {
+  using C = Cfg<H, MT>;
+  const int L = g.L;
+  const int n_img = 2 * L - 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_img * H * H) return;
+  const int img = (int)(idx / (H * H)), n = (int)(idx % (H * H)) / H, k = (int)(idx % H);
+  float v = 0.f;
+  uint32_t nrows = C::NB;
+  if (img < L - 1) {                 // WF_l, l = img + 1: B[n = j_out][k = k_in] = W_l[j][k]
+    const int l = img + 1, fo = 3 * H + (l - 1) * (H * H + H);
+    v = flat[fo + n * H + k];
+  } else if (img == L - 1) {         // output layer: rows o < n_out of 16
+    if (n >= 16) return;
+    nrows = 16;
+    const int fo = 3 * H + (L - 1) * (H * H + H);
+    if (n < g.n_out) v = flat[fo + n * H + k];
+  } else {                           // WB_l, l = 2L - 1 - img: B[n = k_in][k = j_out] = W_l[j_out][k_in]
+    const int l = 2 * L - 1 - img, fo = 3 * H + (l - 1) * (H * H + H);
+    v = flat[fo + k * H + n];
+  }
+  float hi, lo;
+  split_tf32(v, hi, lo);
+  const size_t off = (size_t)img * C::WSTAGE + (size_t)(k / (8 * C::GK)) * C::WBLK + (size_t)((k % (8 * C::GK)) / 8) * (nrows * 32) +
+                     (size_t)(n >> 3) * 256 + (size_t)((k >> 2) & 1) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4;
+  *reinterpret_cast<float*>(wimg + off) = hi;
+  *reinterpret_cast<float*>(wimg + off + (size_t)C::NG * C::WBLK) = lo;
+}
+
+struct PmState {
+  uint8_t* wimg = nullptr;
+  float* stash = nullptr;
+  long long* dbg = nullptr;
+  int dbg_on = 0, last_grid = 0, grid = 0;
+  size_t wstage = 0;
+};
+
+typedef void (*PmKernel)(const PArgs);
+template <int H, int MT, int L>
+PmKernel pm_kernel_of(bool train) { return train ? nsf_pm_jet_kernel<H, L, MT, true> : nsf_pm_jet_kernel<H, L, MT, false>; }
+PmKernel pm_kernel(int H, int L, bool train) {
+  if (H == 80) {
+    switch (L) {
+      case 2: return pm_kernel_of<80, 128, 2>(train);
+      case 3: return pm_kernel_of<80, 128, 3>(train);
+      case 4: return pm_kernel_of<80, 128, 4>(train);
+      case 5: return pm_kernel_of<80, 128, 5>(train);
+      default: return pm_kernel_of<80, 128, 6>(train);
+    }
+  }
+  switch (L) {
+    case 2: return pm_kernel_of<120, 64, 2>(train);
+    case 3: return pm_kernel_of<120, 64, 3>(train);
+    default: return pm_kernel_of<120, 64, 4>(train);
+  }
+}
+
+}  // namespace
+
+int nsf_pm_supported(const NsfNetGeom& g) {
+  if (g.n_out != 3 || g.L < 2) return 0;
+  return (g.H == 80 && g.L <= 6) || (g.H == 120 && g.L <= 4);
+}
+
+// collocation points of one tile
+int nsf_pm_tile_points(const NsfNetGeom& g) { return g.H == 80 ? Cfg<80, 128>::PTS : Cfg<120, 64>::PTS; }
+
+int nsf_pm_init(NsfCtx* ctx) {
+  if (ctx->pm) return NSF_OK;
+  const NsfNetGeom& g = ctx->main.g;
+  if (!nsf_pm_supported(g)) { nsf_set_error("tcgen05 path covers hidden = 80 (2..6 hidden layers) and hidden = 120 (2..4)"); return NSF_E_SHAPE; }
+  PmState* s = new PmState();
+  s->grid = ctx->sms < ctx->main.rows ? ctx->sms : ctx->main.rows;
+  const size_t smem = g.H == 80 ? Cfg<80, 128>::SMEM_BYTES : Cfg<120, 64>::SMEM_BYTES;
+  s->wstage = g.H == 80 ? Cfg<80, 128>::WSTAGE : Cfg<120, 64>::WSTAGE;
+  const size_t wbytes = (size_t)(2 * g.L - 1) * s->wstage;
+  const size_t sbytes = (size_t)s->grid * g.L * nsf_pm_tile_points(g) * g.H * 4 * sizeof(float);
+  NSF_CUDA_OK(cudaMalloc((void**)&s->wimg, wbytes));
+  NSF_CUDA_OK(cudaMemset(s->wimg, 0, wbytes));
+  NSF_CUDA_OK(cudaMalloc((void**)&s->stash, sbytes));
+  for (int train = 0; train < 2; ++train)
+    NSF_CUDA_OK(cudaFuncSetAttribute(pm_kernel(g.H, g.L, train != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctx->ws_bytes += (long long)(wbytes + sbytes);
+  ctx->pm = s;
+  return NSF_OK;
+}
+
+void nsf_pm_free(NsfCtx* ctx) {
+  PmState* s = (PmState*)ctx->pm;
+  if (!s) return;
+  cudaFree(s->wimg); cudaFree(s->stash); if (s->dbg) cudaFree(s->dbg);
+  delete s;
+  ctx->pm = nullptr;
+}
+
+// rows (CTAs) the launch for n points writes
+int nsf_pm_grid(NsfCtx* ctx, long long n) {
+  PmState* s = (PmState*)ctx->pm;
+  const int pts = nsf_pm_tile_points(ctx->main.g);
+  const long long tiles = (n + pts - 1) / pts;
+  return (int)(tiles < s->grid ? tiles : s->grid);
+}
+
+int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches) {
+  PmState* s = (PmState*)ctx->pm;
+  const NsfNetGeom& g = ctx->main.g;
+  const long long tot = (long long)(2 * g.L - 1) * g.H * g.H;
+  if (g.H == 80) nsf_pm_pack_kernel<80, 128><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, flat_params, s->wimg);
+  else nsf_pm_pack_kernel<120, 64><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, flat_params, s->wimg);
+  NSF_CUDA_OK(cudaGetLastError());
+  ++*launches;
+  const bool train = k.mode == NSF_MODE_JET_STEP;
+  PArgs a;
+  a.g = g; a.pk = k.pk; a.wimg = s->wimg; a.x = k.x; a.y = k.y; a.n = k.n;
+  a.e_in = k.e_in; a.vtm_in = k.vtm_in; a.vtm_out = k.vtm_out; a.w = k.w;
+  a.inv_Re = k.inv_Re; a.vis_t0 = k.vis_t0; a.alpha_evm = k.alpha_evm; a.cs1 = k.cs1; a.cs2 = k.cs2; a.k4 = k.k4; a.c_eq = k.c_eq;
+  a.has_evm = k.has_evm;
+  a.resid_out = k.resid_out; a.vis_t_out = k.vis_t_out; a.ebar_out = k.ebar_out;
+  a.stash = train ? s->stash : nullptr;
+  a.scratch = train ? k.scratch : nullptr;
+  const int pts = nsf_pm_tile_points(g);
+  a.n_tiles = (int)((k.n + pts - 1) / pts);
+  a.dbg = (s->dbg_on && train) ? s->dbg : nullptr;
+  const int grid = a.n_tiles < s->grid ? a.n_tiles : s->grid;
+  if (grid <= 0) { *grid_out = 0; return NSF_OK; }
+  const size_t smem = g.H == 80 ? Cfg<80, 128>::SMEM_BYTES : Cfg<120, 64>::SMEM_BYTES;
+  const int nthreads = g.H == 80 ? Cfg<80, 128>::NTHREADS : Cfg<120, 64>::NTHREADS;
+  pm_kernel(g.H, g.L, train)<<<grid, nthreads, smem, st>>>(a);
+  NSF_CUDA_OK(cudaGetLastError());
+  ++*launches;
+  s->last_grid = grid;
+  *grid_out = grid;
+  return NSF_OK;
+}
+
+// Diagnostics: enable (out == NULL) or read back the cycle counters of the last launch, averaged over CTAs:
+//   out[0..3]  issuer: wait for operands, issue (incl. weight waits), wait for weights, MMA stages
+//   out[4..6]  epilogue warp 0: wait for D, wait for the weight-gradient MMAs, work;  out[8..10] the same for the last epilogue warp
+int nsf_pm_stage_cycles(NsfCtx* ctx, double* out) {
+  int rc = nsf_pm_init(ctx);
+  if (rc != NSF_OK) return rc;
+  PmState* s = (PmState*)ctx->pm;
+  if (!s->dbg) { NSF_CUDA_OK(cudaMalloc((void**)&s->dbg, (size_t)s->grid * 32 * sizeof(long long))); NSF_CUDA_OK(cudaMemset(s->dbg, 0, (size_t)s->grid * 32 * sizeof(long long))); }
+  s->dbg_on = 1;
+  if (!out) return NSF_OK;
+  NSF_CUDA_OK(cudaDeviceSynchronize());
+  const int n = s->last_grid > 0 ? s->last_grid : 1;
+  long long* h = new long long[(size_t)n * 32];
+  if (cudaMemcpy(h, s->dbg, (size_t)n * 32 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) { delete[] h; nsf_set_error("cudaMemcpy failed"); return NSF_E_CUDA; }
+  for (int i = 0; i < 256; ++i) out[i] = 0.0;
+  for (int i = 0; i < 32; ++i) { double acc = 0; for (int c = 0; c < n; ++c) acc += (double)h[(size_t)c * 32 + i]; out[i] = acc / n; }
+  delete[] h;
+  return NSF_OK;
+}
