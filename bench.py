@@ -141,8 +141,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the 120 000-point Adam-iteration measurement")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 tile-major, 3 tcgen05 layer-major, 4 tcgen05 tile-major with the weights in tensor memory")
-    ap.add_argument("--nt", type=int, default=0, help="tiles per super-batch of the layer-major kernel (0 = default)")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 with the neurons on M (round 1), 3 tcgen05 with the points on M")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -172,8 +171,6 @@ def main():
         P = PysicsInformedNeuralNetwork(Re=1000, layers=4, hidden_size=120, N_f=args.n_f * world, bc_weight=10, eq_weight=1)
     if args.path:
         P._ctx.set_path(args.path)
-    if args.nt:
-        P._ctx.set_tiles_per_batch(args.nt)
     P.log_interval = 10 ** 9
     P.checkpoints = False
     P.set_boundary_data(cavity_boundary(513))
@@ -321,7 +318,7 @@ def main():
     peak = 0.5 * bf16_sust          # dense TF32 = 1/2 of the measured sustained bf16 (kernel timed inside a long step)
     info = P._ctx.info()
     cfg = workload_config(args)
-    cfg["kernel_path"] = {1: "ffma", 2: "tcgen05-3xtf32 tile-major", 3: "tcgen05-3xtf32 layer-major", 4: "tcgen05-3xtf32 tile-major, weights in tensor memory"}[info["path"]]
+    cfg["kernel_path"] = {1: "ffma", 2: "tcgen05-3xtf32, neurons on M (8-point tiles)", 3: "tcgen05-3xtf32, points on M (32 / 16-point tiles)"}[info["path"]]
     line = {"metric": "collocation_pts_per_s (residual + weight gradient)", "value": value, "unit": "pts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,

@@ -55,8 +55,9 @@ struct Cfg {
   static constexpr int NSUB = MT == 128 ? 4 : 3; // epilogue warps per TMEM quadrant
   static constexpr int NEW = 4 * NSUB;           // epilogue warps
   static constexpr int NWORK = MT == 128 ? NSUB : 2 * NSUB;  // workers (warps resp. half-warps) per quadrant
-  static constexpr int NPW = H / NWORK;          // neurons per worker
-  static constexpr int NCH = NPW / 4;            // 4-neuron chunks per worker
+  static constexpr int CW = 4 * NWORK;           // neurons per chunk: chunk c = neurons [CW c, CW (c+1)), 4 per worker
+  static constexpr int NCH = H / CW;             // chunks per stage (= 4-neuron pieces per worker)
+  static constexpr int KPC = CW / 8;             // k-steps of the next contraction that one chunk completes
   static constexpr int NEPI = NEW * 32;
   static constexpr int NTHREADS = (NEW + 2) * 32;
   static constexpr uint32_t GRP = (H / 4) * 512; // one 32-row group of one image part
@@ -71,7 +72,7 @@ struct Cfg {
   static constexpr bool GWL_SMEM = MT == 128;   // 18 warps leave 96 registers per thread: the output-layer gradient goes to shared memory
   static constexpr uint32_t MISC = MT == 128 ? 15360 : 12288;
   static constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;
-  static_assert(H % 8 == 0 && KS % GK == 0 && H % NWORK == 0 && NPW % 4 == 0, "shape");
+  static_assert(H % 8 == 0 && KS % GK == 0 && H % CW == 0 && CW % 8 == 0 && NCH <= 5, "shape");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
   static_assert(OFF_Q % 1024 == 0 && OFF_WHI % 1024 == 0 && PART % 1024 == 0, "swizzle phase");
 };
@@ -93,7 +94,7 @@ struct PArgs {
 
 template <int H, int L, int NGWL>
 struct Misc {
-  uint64_t ready;        // operands of the next MMA stage written, previous results consumed (one arrival per epilogue warp)
+  uint64_t ready[5];     // chunk c of the next MMA stage's operands written, previous results consumed (one arrival per epilogue warp)
   uint64_t dfull;        // forward / dgrad MMAs of the stage complete
   uint64_t wdone[4];     // weight-gradient MMAs over row group q complete (P / Q rows of the group may be rewritten)
   uint64_t hi_full[3], hi_free[3], lo_full[2], lo_free[2];
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   if (warp == C::NEW) tmem_alloc(&misc->tmem_base, 512);
   if (tid == 0) {
     if (smem_base & 1023u) __trap();
-    mbar_init(&misc->ready, C::NEW); mbar_init(&misc->dfull, 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&misc->ready[i], C::NEW);
+    mbar_init(&misc->dfull, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&misc->wdone[i], 1);
     for (int i = 0; i < 3; ++i) { mbar_init(&misc->hi_full[i], 1); mbar_init(&misc->hi_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&misc->lo_full[i], 1); mbar_init(&misc->lo_free[i], 1); }
@@ -213,29 +215,39 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         const uint32_t idesc = idesc_tf32(MT, outst ? 16 : C::NB, 1, 0);
         const uint32_t d_col = tmem + DCOL;
         long long t0 = 0, t1 = 0;
-        if (dbg) t0 = clock64();
-        mbar_wait(&misc->ready, ready_ph); ready_ph ^= 1u;
-        tc_fence_after();
-        if (dbg) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
         const uint32_t a_hi = sb4 + (C::OFF_P >> 4) + lbo_field(C::GRP), a_lo = a_hi + (C::PART >> 4);
-        // correction products first (the tensor core truncates when it adds into the accumulator: small terms while it is small)
+        // The epilogue hands the operand image over chunk by chunk (CW neurons = KPC k-steps of this contraction): the two
+        // correction products of a k-step (lo * hi, hi * lo) are issued as soon as its neurons are written and run under the
+        // epilogue; the hi * hi products follow when the image is complete.  Corrections first on purpose: the tensor core
+        // TRUNCATES when it adds into the fp32 accumulator, so the 2^-11-sized terms go in while the accumulator is small
+        // (10 full-magnitude accumulations per layer instead of 30; interleaving the three products per k-step tripled the
+        // residual error and failed the 1e-5 bar on the EVM gradient).
 #pragma unroll
-        for (int gi = 0; gi < C::NG; ++gi) {
-          if (dbg) t1 = clock64();
-          mbar_wait(&misc->hi_full[gi], stage_ctr & 1u);
-          if ((gi & 1) == 0) { mbar_wait(&misc->lo_full[0], lo_ctr0 & 1u); ++lo_ctr0; }
-          else { mbar_wait(&misc->lo_full[1], lo_ctr1 & 1u); ++lo_ctr1; }
-          if (dbg) c_wwait += clock64() - t1;
-          const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
-          const uint32_t w_lo = sb4 + ((C::OFF_WLO + (gi & 1) * C::WBLK) >> 4) + lbo_field(128);
+        for (int c = 0; c < C::NCH; ++c) {
+          if (dbg) t0 = clock64();
+          mbar_wait(&misc->ready[c], ready_ph);
+          tc_fence_after();
+          if (dbg) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
 #pragma unroll
-          for (int kk = 0; kk < C::GK; ++kk) {
-            const uint32_t da = (uint32_t)((gi * C::GK + kk) * 1024) >> 4, dw = (kk * wsub) >> 4;
-            mma_tf32_elect2(d_col, a_lo + da, AHI, w_hi + dw, BHI, idesc, (gi | kk) > 0, leader);
+          for (int kc = 0; kc < C::KPC; ++kc) {
+            const int ks = c * C::KPC + kc, gi = ks / C::GK, kk = ks % C::GK;
+            if (kk == 0) {
+              if (dbg) t1 = clock64();
+              mbar_wait(&misc->hi_full[gi], stage_ctr & 1u);
+              if ((gi & 1) == 0) { mbar_wait(&misc->lo_full[0], lo_ctr0 & 1u); ++lo_ctr0; }
+              else { mbar_wait(&misc->lo_full[1], lo_ctr1 & 1u); ++lo_ctr1; }
+              if (dbg) c_wwait += clock64() - t1;
+            }
+            const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
+            const uint32_t w_lo = sb4 + ((C::OFF_WLO + (gi & 1) * C::WBLK) >> 4) + lbo_field(128);
+            const uint32_t da = (uint32_t)(ks * 1024) >> 4, dw = (kk * wsub) >> 4;
+            mma_tf32_elect2(d_col, a_lo + da, AHI, w_hi + dw, BHI, idesc, ks > 0, leader);
             mma_tf32_elect2(d_col, a_hi + da, AHI, w_lo + dw, BHI, idesc, 1, leader);
+            if (kk == C::GK - 1) mma_commit_elect(&misc->lo_free[gi & 1], leader);
           }
-          mma_commit_elect(&misc->lo_free[gi & 1], leader);
+          if (dbg) c_issue += clock64() - t0;
         }
+        if (dbg) t0 = clock64();
 #pragma unroll
         for (int gi = 0; gi < C::NG; ++gi) {
           const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
@@ -246,6 +258,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           }
           mma_commit_elect(&misc->hi_free[gi], leader);
         }
+        ready_ph ^= 1u;
         mma_commit_elect(&misc->dfull, leader);
         ++stage_ctr;
         if (TRAIN && s > L) {
@@ -309,20 +322,21 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
     const int q = warp & 3, sub = warp >> 2;
     const int l16 = MT == 128 ? lane : (lane & 15);
     const int worker = MT == 128 ? sub : 2 * sub + (lane >> 4);
-    const int nb = C::NPW * worker;                       // first neuron of this worker
-    const int kq = lane & 3;                              // neuron within a chunk (after the transpose) == stream before it
+    const int kq = lane & 3;                              // neuron within a 4-neuron piece (after the transpose) == stream before it
     const int pt_loc = (MT == 128 ? 8 : 4) * q + (l16 >> 2);   // point of the tile this thread works for
     const int rg = MT == 128 ? q : (q >> 1);              // 32-row group of the images its rows are in
     const bool primary = worker == 0;                     // one worker per quadrant does the per-point bookkeeping
     const bool red_lane = l16 < 4;                        // lane that owns the warp-reduced sums of neuron kq
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    // TMEM address of this worker's D columns: chunk c at + 4c (MT = 64: the upper half-warp reads NPW columns further)
-    const uint32_t d_thr = tmem + lane_addr + DCOL + (uint32_t)(MT == 128 ? nb : C::NPW * 2 * sub);
-    // byte offset of this thread's float4 (neuron nb + kq, chunk 0) inside an image part; chunk c: + 512 c
-    const uint32_t img_thr = (uint32_t)(pt_loc >> 3) * C::GRP + (uint32_t)(nb >> 2) * 512u + (uint32_t)kq * 128u +
+    // chunk c = neurons [CW c, CW (c + 1)); this worker's piece of it is neurons CW c + 4 worker + (0..3)
+    // TMEM address of this worker's D columns in chunk 0 (MT = 64: the upper half-warp reads 4 columns further); chunk c: + CW c
+    const uint32_t d_thr = tmem + lane_addr + DCOL + (uint32_t)(MT == 128 ? 4 * worker : 8 * sub);
+    // byte offset of this thread's float4 (neuron 4 worker + kq of chunk 0) inside an image part; chunk c: + CSTR c
+    const uint32_t img_thr = (uint32_t)(pt_loc >> 3) * C::GRP + (uint32_t)worker * 512u + (uint32_t)kq * 128u +
                              (uint32_t)((((pt_loc >> 1) & 3) ^ kq) * 32) + (uint32_t)(pt_loc & 1) * 16u;
+    constexpr uint32_t CSTR = (C::CW / 4) * 512u;
     const uint32_t p_thr = smem_base + C::OFF_P + img_thr, q_thr = smem_base + C::OFF_Q + img_thr;
-    const int k0 = nb + kq;                               // this thread's neuron in chunk 0 (chunk c: + 4c)
+    const int k0 = 4 * worker + kq;                       // this thread's neuron in chunk 0 (chunk c: + CW c)
     const float* pk = a.pk;
     float4* stash_thr = TRAIN ? reinterpret_cast<float4*>(a.stash) + ((size_t)blockIdx.x * L * C::PTS + pt_loc) * H + k0 : nullptr;
     constexpr size_t STL = (size_t)C::PTS * H;            // stash stride between layers (float4)
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
       for (int c = 0; c < C::NCH; ++c) gwl[o][c] = 0.f;
     uint32_t dfull_ph = 0, rs_ctr = 0;
-    long long c_dwait = 0, c_wwait = 0, c_work = 0;
+    long long c_dwait = 0, c_wwait = 0, c_work = 0, c_s0 = 0, c_fwd = 0, c_out = 0, c_ra = 0, c_rb = 0, c_last = 0, c_dw_fwd = 0, c_dw_rev = 0;
 
     auto red_pts = [&](float v) {      // sum over the points of this worker's rows (fixed tree: deterministic)
       v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -340,11 +354,11 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       if (MT == 128) v += __shfl_xor_sync(0xffffffffu, v, 16);
       return v;
     };
-    auto hand_over = [&]() {           // operands visible to the async proxy, TMEM accesses retired -> issuer
+    auto chunk_done = [&](int c) {     // chunk c of the operands visible to the async proxy, TMEM accesses retired -> issuer
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&misc->ready);
+      if (lane == 0) mbar_arrive(&misc->ready[c]);
     };
 
     for (int t = 0; t < my_tiles; ++t) {
@@ -357,44 +371,49 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       // ---------------- stage 0: layer 0 (K = 2) ----------------
 #pragma unroll
       for (int c = 0; c < C::NCH; ++c) {
-        const int k = k0 + 4 * c;
+        const int k = k0 + C::CW * c;
         const float w0x = __ldg(pk + g.pk_w0x() + k), w0y = __ldg(pk + g.pk_w0y() + k), b0 = __ldg(pk + g.pk_b0() + k);
         const float z[4] = {fmaf(w0x, xv, fmaf(w0y, yv, b0)), w0x, w0y, 0.f};
         float v[4];
         nsf_jet_fwd(z, v);
-        store_jet<C::PART>(p_thr + 512u * c, v);
-        if (TRAIN) __stcg(stash_thr + 4 * c, make_float4(v[0], z[1], z[2], z[3]));
+        store_jet<C::PART>(p_thr + CSTR * c, v);
+        if (TRAIN) __stcg(stash_thr + C::CW * c, make_float4(v[0], z[1], z[2], z[3]));
+        chunk_done(c);
       }
-      hand_over();
-      if (dbg) { t1 = clock64(); c_work += t1 - t0; }
+      if (dbg) { t1 = clock64(); c_work += t1 - t0; c_s0 += t1 - t0; }
       // ---------------- stages 1 .. L-1: hidden layers forward ----------------
 #pragma unroll 1
       for (int s = 1; s < L; ++s) {
         float bias[C::NCH];
 #pragma unroll
-        for (int c = 0; c < C::NCH; ++c) bias[c] = __ldg(pk + g.pk_b(s) + k0 + 4 * c);
+        for (int c = 0; c < C::NCH; ++c) bias[c] = __ldg(pk + g.pk_b(s) + k0 + C::CW * c);
         if (dbg) t0 = clock64();
         mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
         tc_fence_after();
-        if (dbg) { t1 = clock64(); c_dwait += t1 - t0; }
+        if (dbg) { t1 = clock64(); c_dwait += t1 - t0; c_dw_fwd += t1 - t0; }
         float d[C::NCH][4];
 #pragma unroll
-        for (int c = 0; c < C::NCH; ++c) ld_d4<MT, C::NPW>(d_thr + 4 * c, d[c]);
+        for (int c = 0; c < C::NCH; ++c) ld_d4<MT, 4>(d_thr + C::CW * c, d[c]);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < C::NCH; ++c) {
-          float z[4], v[4];
+        for (int c = 0; c < C::NCH; ++c) {      // all transposes first: the hand-over fences below pin the shuffles in place
+          float z[4];
           quad_transpose(d[c], z, lane);
-          z[0] += bias[c];
-          nsf_jet_fwd(z, v);
-          store_jet<C::PART>(p_thr + 512u * c, v);
-          if (TRAIN) __stcg(stash_thr + s * STL + 4 * c, make_float4(v[0], z[1], z[2], z[3]));
+          d[c][0] = z[0] + bias[c]; d[c][1] = z[1]; d[c][2] = z[2]; d[c][3] = z[3];
         }
-        hand_over();
-        if (dbg) c_work += clock64() - t1;
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) {
+          float v[4];
+          nsf_jet_fwd(d[c], v);
+          store_jet<C::PART>(p_thr + CSTR * c, v);
+          if (TRAIN) __stcg(stash_thr + s * STL + C::CW * c, make_float4(v[0], d[c][1], d[c][2], d[c][3]));
+          chunk_done(c);
+        }
+        if (dbg) { t0 = clock64(); c_work += t0 - t1; c_fwd += t0 - t1; }
       }
       // ---------------- stage L: output layer, residuals, adjoint seeds ----------------
       float ob[4][3];      // adjoint of the outputs: [stream][u, v, p]
+      float4 stl[C::NCH];  // stash of layer L-1 (this thread's neurons), for the output layer's backward
       {
         float pre_e = 0.f, pre_vtm = a.vis_t0, pre_w = 1.f;
         if (ok) {
@@ -402,10 +421,14 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           if (a.w) pre_w = __ldg(a.w + gp);
         }
         const float bo0 = __ldg(pk + g.pk_bl() + 0), bo1 = __ldg(pk + g.pk_bl() + 1), bo2 = __ldg(pk + g.pk_bl() + 2);
+        if (TRAIN) {
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) stl[c] = __ldcg(stash_thr + (L - 1) * STL + C::CW * c);
+        }
         if (dbg) t0 = clock64();
         mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
         tc_fence_after();
-        if (dbg) { t1 = clock64(); c_dwait += t1 - t0; }
+        if (dbg) { t1 = clock64(); c_dwait += t1 - t0; c_dw_fwd += t1 - t0; }
         float o[4];
         ld_d4<MT, 4>(tmem + lane_addr + DCOL, o);           // this row's (u, v, p, -) of stream kq
         tmem_ld_wait();
@@ -467,13 +490,14 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       }
       if (TRAIN) {
         {
-          // output layer backward on FFMA (3 outputs): adjoint of a_{L-1}, weight gradient of the output layer
-          float4 stl[C::NCH];
+          // output layer backward on FFMA (3 outputs): adjoint of a_{L-1}, weight gradient of the output layer.
+          // a_{L-2} (second operand of the next weight gradient) comes from the stash alone: its loads fly meanwhile.
+          float4 stm[C::NCH];
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) stl[c] = __ldcg(stash_thr + (L - 1) * STL + 4 * c);
+          for (int c = 0; c < C::NCH; ++c) stm[c] = __ldcg(stash_thr + (L - 2) * STL + C::CW * c);
 #pragma unroll
           for (int c = 0; c < C::NCH; ++c) {
-            const int k = k0 + 4 * c;
+            const int k = k0 + C::CW * c;
             const float wl0 = __ldg(pk + g.pk_wl() + k), wl1 = __ldg(pk + g.pk_wl() + g.HP + k), wl2 = __ldg(pk + g.pk_wl() + 2 * g.HP + k);
             float ab[4], act[4], zb[4];
 #pragma unroll
@@ -497,35 +521,34 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
               for (int o = 0; o < 3; ++o) gwl[o][c] += gl[o];
             }
             nsf_zbar_from(stl[c], ab, zb);
-            store_jet<C::PART>(p_thr + 512u * c, zb);
             const float sb0 = red_pts(zb[0]);
             if (red_lane) misc->gb[q][L - 1][k] += sb0;
-          }
-          float4 stm[C::NCH];
+            store_jet<C::PART>(p_thr + CSTR * c, zb);
+            if (c == C::NCH - 1) {      // Q is read by the weight-gradient MMAs only, issued after the last chunk of P
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) stm[c] = __ldcg(stash_thr + (L - 2) * STL + 4 * c);
-#pragma unroll
-          for (int c = 0; c < C::NCH; ++c) {
-            float am[4];
-            nsf_act_from_stash(stm[c], am);
-            store_jet<C::PART>(q_thr + 512u * c, am);
+              for (int cc = 0; cc < C::NCH; ++cc) {
+                float am[4];
+                nsf_act_from_stash(stm[cc], am);
+                store_jet<C::PART>(q_thr + CSTR * cc, am);
+              }
+            }
+            chunk_done(c);
           }
-          hand_over();
-          if (dbg) c_work += clock64() - t1;
+          if (dbg) { t0 = clock64(); c_work += t0 - t1; c_out += t0 - t1; }
         }
         // ---------------- stages L+1 .. 2L-1: reverse of hidden layer l = L-1 .. 1; D = adjoint of a_{l-1} ----------------
 #pragma unroll 1
         for (int lm1 = L - 2; lm1 >= 0; --lm1) {       // lm1 = l - 1: the layer whose tanh is differentiated in this stage
           float4 st1[C::NCH];
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + lm1 * STL + 4 * c);
+          for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + lm1 * STL + C::CW * c);
           if (dbg) t0 = clock64();
           mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
           tc_fence_after();
-          if (dbg) { t1 = clock64(); c_dwait += t1 - t0; }
+          if (dbg) { t1 = clock64(); c_dwait += t1 - t0; c_dw_rev += t1 - t0; }
           float d[C::NCH][4];
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) ld_d4<MT, C::NPW>(d_thr + 4 * c, d[c]);
+          for (int c = 0; c < C::NCH; ++c) ld_d4<MT, 4>(d_thr + C::CW * c, d[c]);
           tmem_ld_wait();
           if (lm1 >= 1) {
 #pragma unroll
@@ -534,36 +557,41 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
               quad_transpose(d[c], ab, lane);
               nsf_zbar_from(st1[c], ab, zb);
               const float sb0 = red_pts(zb[0]);
-              if (red_lane) misc->gb[q][lm1][k0 + 4 * c] += sb0;
-              st_d4<MT, C::NPW>(d_thr + 4 * c, zb);     // park zbar_{l-1} in this thread's own (now free) D cells
+              if (red_lane) misc->gb[q][lm1][k0 + C::CW * c] += sb0;
+              st_d4<MT, 4>(d_thr + C::CW * c, zb);     // park zbar_{l-1} in this thread's own (now free) D cells
             }
             // a_{l-2} comes from the stash alone; the loads fly while this warp waits for the weight-gradient MMAs
 #pragma unroll
-            for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + (lm1 - 1) * STL + 4 * c);
+            for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + (lm1 - 1) * STL + C::CW * c);
             tmem_st_wait();
-            if (dbg) { t0 = clock64(); c_work += t0 - t1; }
+            if (dbg) { t0 = clock64(); c_work += t0 - t1; c_ra += t0 - t1; }
             // the weight-gradient MMAs of this stage still read P and Q: wait for those over this thread's rows
             mbar_wait(&misc->wdone[rg], rs_ctr & 1u);
             ++rs_ctr;
             if (dbg) { t1 = clock64(); c_wwait += t1 - t0; }
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < C::NCH; ++c) ld_d4<MT, C::NPW>(d_thr + 4 * c, d[c]);
+            for (int c = 0; c < C::NCH; ++c) ld_d4<MT, 4>(d_thr + C::CW * c, d[c]);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < C::NCH; ++c) {
-              float am[4];
-              store_jet<C::PART>(p_thr + 512u * c, d[c]);
-              nsf_act_from_stash(st1[c], am);
-              store_jet<C::PART>(q_thr + 512u * c, am);
+              store_jet<C::PART>(p_thr + CSTR * c, d[c]);
+              if (c == C::NCH - 1) {    // Q is read by the weight-gradient MMAs only, issued after the last chunk of P
+#pragma unroll
+                for (int cc = 0; cc < C::NCH; ++cc) {
+                  float am[4];
+                  nsf_act_from_stash(st1[cc], am);
+                  store_jet<C::PART>(q_thr + CSTR * cc, am);
+                }
+              }
+              chunk_done(c);
             }
-            hand_over();
-            if (dbg) c_work += clock64() - t1;
+            if (dbg) { t0 = clock64(); c_work += t0 - t1; c_rb += t0 - t1; }
           } else {
             // layer 0: its weight gradient (K = 2) and bias gradient on FFMA; nothing goes back to the tensor core
 #pragma unroll
             for (int c = 0; c < C::NCH; ++c) {
-              const int k = k0 + 4 * c;
+              const int k = k0 + C::CW * c;
               float ab[4], zb[4];
               quad_transpose(d[c], ab, lane);
               nsf_zbar_from(st1[c], ab, zb);
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
               const float sx = red_pts(fmaf(zb[0], xv, zb[1])), sy = red_pts(fmaf(zb[0], yv, zb[2]));
               if (red_lane) { misc->gb[q][0][k] += sb0; misc->gw0x[q][k] += sx; misc->gw0y[q][k] += sy; }
             }
-            if (dbg) { t0 = clock64(); c_work += t0 - t1; }
+            if (dbg) { t0 = clock64(); c_work += t0 - t1; c_last += t0 - t1; }
             // every weight-gradient MMA of the tile: P and Q are rewritten by the next tile's stage 0 / output stage, and the flush follows
 #pragma unroll
             for (int i = 0; i < C::NQ; ++i) mbar_wait(&misc->wdone[i], rs_ctr & 1u);
@@ -613,7 +641,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
     }
     if (dbg && lane == 0) {
       long long* d = a.dbg + (size_t)blockIdx.x * 32 + 4;
-      if (warp == 0) { d[0] = c_dwait; d[1] = c_wwait; d[2] = c_work; }
+      if (warp == 0) { d[0] = c_dwait; d[1] = c_wwait; d[2] = c_work; d[8] = c_s0; d[9] = c_fwd; d[10] = c_out; d[11] = c_ra; d[12] = c_rb; d[13] = c_last; d[14] = c_dw_fwd; d[15] = c_dw_rev; }
       if (warp == C::NEW - 1) { d[4] = c_dwait; d[5] = c_wwait; d[6] = c_work; }
     }
     // ---- CTA epilogue: per-quadrant accumulators and per-thread partials -> this CTA's gradient row ----
@@ -626,7 +654,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             const float vsum = red_pts(gwl[o][c]);
-            if (red_lane) gwls[(q * 3 + o) * H + k0 + 4 * c] = vsum;
+            if (red_lane) gwls[(q * 3 + o) * H + k0 + C::CW * c] = vsum;
           }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(C::NEPI) : "memory");
