@@ -89,6 +89,7 @@ struct PArgs {
   float* stash;          // [grid][L][PTS][H] float4
   float* scratch;        // gradient rows [grid][gs_row]
   int n_tiles;
+  int ho_mask;           // bit c set: the epilogue hands the operand image over after chunk c (bit NCH-1 always set)
   long long* dbg;        // optional [grid][32] cycle counters
 };
 
@@ -222,11 +223,17 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         // TRUNCATES when it adds into the fp32 accumulator, so the 2^-11-sized terms go in while the accumulator is small
         // (10 full-magnitude accumulations per layer instead of 30; interleaving the three products per k-step tripled the
         // residual error and failed the 1e-5 bar on the EVM gradient).
+        int ready_upto = -1;      // chunks [0, ready_upto] have been handed over
 #pragma unroll
         for (int c = 0; c < C::NCH; ++c) {
           if (dbg) t0 = clock64();
-          mbar_wait(&misc->ready[c], ready_ph);
-          tc_fence_after();
+          if (c > ready_upto) {
+            int e = c;
+            while (!((a.ho_mask >> e) & 1)) ++e;
+            mbar_wait_relaxed(&misc->ready[e], ready_ph, 32);
+            tc_fence_after();
+            ready_upto = e;
+          }
           if (dbg) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
 #pragma unroll
           for (int kc = 0; kc < C::KPC; ++kc) {
@@ -299,16 +306,16 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         const uint32_t blk = (img == L - 1) ? C::WBLK_O : C::WBLK;
 #pragma unroll
         for (int gi = 0; gi < C::NG; ++gi) {
-          if (n >= 1) mbar_wait(&misc->hi_free[gi], (uint32_t)((n - 1) & 1));
+          if (n >= 1) mbar_wait_relaxed(&misc->hi_free[gi], (uint32_t)((n - 1) & 1), 200);
           mbar_expect_tx(&misc->hi_full[gi], blk);
           tma_bulk_g2s(smem + C::OFF_WHI + gi * C::WBLK, src + (size_t)gi * C::WBLK, blk, &misc->hi_full[gi]);
           if ((gi & 1) == 0) {
-            if (lo_use0 >= 1) mbar_wait(&misc->lo_free[0], (lo_use0 - 1) & 1u);
+            if (lo_use0 >= 1) mbar_wait_relaxed(&misc->lo_free[0], (lo_use0 - 1) & 1u, 200);
             ++lo_use0;
             mbar_expect_tx(&misc->lo_full[0], blk);
             tma_bulk_g2s(smem + C::OFF_WLO, src + (size_t)(C::NG + gi) * C::WBLK, blk, &misc->lo_full[0]);
           } else {
-            if (lo_use1 >= 1) mbar_wait(&misc->lo_free[1], (lo_use1 - 1) & 1u);
+            if (lo_use1 >= 1) mbar_wait_relaxed(&misc->lo_free[1], (lo_use1 - 1) & 1u, 200);
             ++lo_use1;
             mbar_expect_tx(&misc->lo_full[1], blk);
             tma_bulk_g2s(smem + C::OFF_WLO + C::WBLK, src + (size_t)(C::NG + gi) * C::WBLK, blk, &misc->lo_full[1]);
@@ -354,7 +361,8 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       if (MT == 128) v += __shfl_xor_sync(0xffffffffu, v, 16);
       return v;
     };
-    auto chunk_done = [&](int c) {     // chunk c of the operands visible to the async proxy, TMEM accesses retired -> issuer
+    auto chunk_done = [&](int c) {     // chunks up to c of the operands visible to the async proxy, TMEM accesses retired -> issuer
+      if (!((a.ho_mask >> c) & 1)) return;
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       long long t0 = 0, t1 = 0;
       if (dbg) t0 = clock64();
       // ---------------- stage 0: layer 0 (K = 2) ----------------
+      float4 st0[C::NCH];
 #pragma unroll
       for (int c = 0; c < C::NCH; ++c) {
         const int k = k0 + C::CW * c;
@@ -377,8 +386,12 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         float v[4];
         nsf_jet_fwd(z, v);
         store_jet<C::PART>(p_thr + CSTR * c, v);
-        if (TRAIN) __stcg(stash_thr + C::CW * c, make_float4(v[0], z[1], z[2], z[3]));
+        st0[c] = make_float4(v[0], z[1], z[2], z[3]);
         chunk_done(c);
+      }
+      if (TRAIN) {      // the stash goes to L2 after the hand-overs: fence.proxy.async would wait for these stores
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) __stcg(stash_thr + C::CW * c, st0[c]);
       }
       if (dbg) { t1 = clock64(); c_work += t1 - t0; c_s0 += t1 - t0; }
       // ---------------- stages 1 .. L-1: hidden layers forward ----------------
@@ -406,14 +419,21 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           float v[4];
           nsf_jet_fwd(d[c], v);
           store_jet<C::PART>(p_thr + CSTR * c, v);
-          if (TRAIN) __stcg(stash_thr + s * STL + C::CW * c, make_float4(v[0], d[c][1], d[c][2], d[c][3]));
+          d[c][0] = v[0];
           chunk_done(c);
+        }
+        if (TRAIN) {    // (t, zx, zy, z_lap) to L2 after the hand-overs: fence.proxy.async would wait for these stores
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) __stcg(stash_thr + s * STL + C::CW * c, make_float4(d[c][0], d[c][1], d[c][2], d[c][3]));
         }
         if (dbg) { t0 = clock64(); c_work += t0 - t1; c_fwd += t0 - t1; }
       }
       // ---------------- stage L: output layer, residuals, adjoint seeds ----------------
       float ob[4][3];      // adjoint of the outputs: [stream][u, v, p]
+      float res_mine = 0.f, res_vis = 0.f, res_vtm = 0.f, res_eb = 0.f;   // per-point results, written to global memory after the hand-overs
       float4 stl[C::NCH];  // stash of layer L-1 (this thread's neurons), for the output layer's backward
+      float4 stc[C::NCH];  // stash of the layer below the one being differentiated: loaded once, used for the second operand of the
+                           // weight gradient (a_{l-2}) and, one stage later, for the adjoint through its tanh
       {
         float pre_e = 0.f, pre_vtm = a.vis_t0, pre_w = 1.f;
         if (ok) {
@@ -463,19 +483,14 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         ob[1][0] = a.cs1 * (g1 * u + g3); ob[1][1] = a.cs1 * (g2 * u); ob[1][2] = a.cs1 * g1;
         ob[2][0] = a.cs1 * (g1 * v); ob[2][1] = a.cs1 * (g2 * v + g3); ob[2][2] = a.cs1 * g2;
         ob[3][0] = -a.cs2 * nu * g1; ob[3][1] = -a.cs2 * nu * g2; ob[3][2] = 0.f;
-        if (sub == 0) {                                     // warp-uniform: one warp per quadrant does the per-point bookkeeping
-          if (primary && ok) {                              // (MT = 64: its lower half-warp; the upper one works for the same rows)
-            if (a.resid_out) {
-              const float e4[4] = {eq1, eq2, eq3, eq4};
-              float mine = e4[0];
+        {
+          const float e4[4] = {eq1, eq2, eq3, eq4};
+          res_mine = e4[0];
 #pragma unroll
-              for (int i = 1; i < 4; ++i) mine = kq == i ? e4[i] : mine;
-              a.resid_out[(long long)kq * a.n + gp] = mine;
-            }
-            if (kq == 0 && a.vis_t_out) a.vis_t_out[gp] = vis;
-            if (kq == 1 && a.has_evm && a.vtm_out) a.vtm_out[gp] = a.alpha_evm * fabsf(ee);
-            if (TRAIN && kq == 2 && a.ebar_out) a.ebar_out[gp] = -g4;
-          }
+          for (int i = 1; i < 4; ++i) res_mine = kq == i ? e4[i] : res_mine;
+          res_vis = vis; res_vtm = a.alpha_evm * fabsf(ee); res_eb = -g4;
+        }
+        if (sub == 0) {                                     // warp-uniform: one warp per quadrant does the per-point bookkeeping
           // loss sums of this quadrant's points (lanes with kq == 0 carry one point each)
           const bool own = primary && kq == 0, cnt = own && ok;
           const float r[9] = {cnt ? pre_w * eq1 * eq1 : 0.f, cnt ? pre_w * eq2 * eq2 : 0.f, cnt ? pre_w * eq3 * eq3 : 0.f, cnt ? pre_w * eq4 * eq4 : 0.f,
@@ -488,13 +503,21 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         }
         if (!TRAIN) { if (dbg) c_work += clock64() - t1; }
       }
+      auto write_point_results = [&]() {   // (MT = 64: the lower half-warp; the upper one works for the same rows)
+        if (primary && ok) {
+          if (a.resid_out) a.resid_out[(long long)kq * a.n + gp] = res_mine;
+          if (kq == 0 && a.vis_t_out) a.vis_t_out[gp] = res_vis;
+          if (kq == 1 && a.has_evm && a.vtm_out) a.vtm_out[gp] = res_vtm;
+          if (TRAIN && kq == 2 && a.ebar_out) a.ebar_out[gp] = res_eb;
+        }
+      };
+      if (!TRAIN) write_point_results();
       if (TRAIN) {
         {
           // output layer backward on FFMA (3 outputs): adjoint of a_{L-1}, weight gradient of the output layer.
           // a_{L-2} (second operand of the next weight gradient) comes from the stash alone: its loads fly meanwhile.
-          float4 stm[C::NCH];
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) stm[c] = __ldcg(stash_thr + (L - 2) * STL + C::CW * c);
+          for (int c = 0; c < C::NCH; ++c) stc[c] = __ldcg(stash_thr + (L - 2) * STL + C::CW * c);
 #pragma unroll
           for (int c = 0; c < C::NCH; ++c) {
             const int k = k0 + C::CW * c;
@@ -528,20 +551,18 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
               for (int cc = 0; cc < C::NCH; ++cc) {
                 float am[4];
-                nsf_act_from_stash(stm[cc], am);
+                nsf_act_from_stash(stc[cc], am);
                 store_jet<C::PART>(q_thr + CSTR * cc, am);
               }
             }
             chunk_done(c);
           }
+          write_point_results();
           if (dbg) { t0 = clock64(); c_work += t0 - t1; c_out += t0 - t1; }
         }
         // ---------------- stages L+1 .. 2L-1: reverse of hidden layer l = L-1 .. 1; D = adjoint of a_{l-1} ----------------
 #pragma unroll 1
         for (int lm1 = L - 2; lm1 >= 0; --lm1) {       // lm1 = l - 1: the layer whose tanh is differentiated in this stage
-          float4 st1[C::NCH];
-#pragma unroll
-          for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + lm1 * STL + C::CW * c);
           if (dbg) t0 = clock64();
           mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
           tc_fence_after();
@@ -555,14 +576,14 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
             for (int c = 0; c < C::NCH; ++c) {
               float ab[4], zb[4];
               quad_transpose(d[c], ab, lane);
-              nsf_zbar_from(st1[c], ab, zb);
+              nsf_zbar_from(stc[c], ab, zb);
               const float sb0 = red_pts(zb[0]);
               if (red_lane) misc->gb[q][lm1][k0 + C::CW * c] += sb0;
               st_d4<MT, 4>(d_thr + C::CW * c, zb);     // park zbar_{l-1} in this thread's own (now free) D cells
             }
             // a_{l-2} comes from the stash alone; the loads fly while this warp waits for the weight-gradient MMAs
 #pragma unroll
-            for (int c = 0; c < C::NCH; ++c) st1[c] = __ldcg(stash_thr + (lm1 - 1) * STL + C::CW * c);
+            for (int c = 0; c < C::NCH; ++c) stc[c] = __ldcg(stash_thr + (lm1 - 1) * STL + C::CW * c);
             tmem_st_wait();
             if (dbg) { t0 = clock64(); c_work += t0 - t1; c_ra += t0 - t1; }
             // the weight-gradient MMAs of this stage still read P and Q: wait for those over this thread's rows
@@ -580,7 +601,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
                 for (int cc = 0; cc < C::NCH; ++cc) {
                   float am[4];
-                  nsf_act_from_stash(st1[cc], am);
+                  nsf_act_from_stash(stc[cc], am);
                   store_jet<C::PART>(q_thr + CSTR * cc, am);
                 }
               }
@@ -594,7 +615,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
               const int k = k0 + C::CW * c;
               float ab[4], zb[4];
               quad_transpose(d[c], ab, lane);
-              nsf_zbar_from(st1[c], ab, zb);
+              nsf_zbar_from(stc[c], ab, zb);
               const float sb0 = red_pts(zb[0]);
               const float sx = red_pts(fmaf(zb[0], xv, zb[1])), sy = red_pts(fmaf(zb[0], yv, zb[2]));
               if (red_lane) { misc->gb[q][0][k] += sb0; misc->gw0x[q][k] += sx; misc->gw0y[q][k] += sy; }
@@ -807,6 +828,10 @@ int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params,
   a.scratch = train ? k.scratch : nullptr;
   const int pts = nsf_pm_tile_points(g);
   a.n_tiles = (int)((k.n + pts - 1) / pts);
+  {
+    static const int ho_env = [] { const char* v = getenv("NSF_PM_HO"); return v ? atoi(v) : 0x15; }();   // hand-over after chunks 0, 2, 4
+    a.ho_mask = (ho_env & 0x1f) | 0x10;
+  }
   a.dbg = (s->dbg_on && train) ? s->dbg : nullptr;
   const int grid = a.n_tiles < s->grid ? a.n_tiles : s->grid;
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }

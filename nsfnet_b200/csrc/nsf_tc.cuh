@@ -41,6 +41,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// same, but the spinning warp sleeps between probes: for the single-warp roles (issuer, weight producer) that share an SM
+// sub-partition with four working epilogue warps and would otherwise take issue slots from them
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- fences ---------------------------------------------------------------------------------
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma operand reads)
