@@ -10,9 +10,12 @@
  * Conventions
  *   - every function returns an int status (NSF_OK == 0, negative == error) and never throws;
  *     nsf_last_error() returns a thread-local message for the last failure on this thread;
- *   - every buffer is a caller-owned CUDA *device* pointer, fp32, contiguous, 16-byte aligned
- *     (what `tensor.data_ptr()` gives for a fresh torch CUDA tensor); nothing is retained after
- *     the call returns except inside the opaque context;
+ *   - every buffer is a caller-owned CUDA *device* pointer, fp32, contiguous; nothing is retained after
+ *     the call returns except inside the opaque context.  PER-POINT arrays (coordinates, targets,
+ *     weights, lagged viscosity, per-point outputs) must be 16-byte aligned -- what `tensor.data_ptr()`
+ *     gives for a fresh torch CUDA tensor, NOT for an odd-offset slice such as x[1:] -- and a
+ *     misaligned one is rejected with NSF_E_ARG; parameter, gradient and loss buffers need 4-byte
+ *     alignment only (they may be offset views of one flat buffer);
  *   - all work is enqueued asynchronously on the caller-supplied `cudaStream_t` (passed as
  *     void*; NULL = legacy default stream); results are ready when the stream reaches that point;
  *   - flat parameter / gradient order is FCNet's state_dict order (net.py:38-46):
@@ -210,6 +213,14 @@ int nsf_wall_distance(const float* x, const float* y, int64_t n, const float* xb
                       float* dist_out, void* stream);
 int nsf_sdf_weights(const float* x, const float* y, int64_t n, const float* xb, const float* yb, int32_t n_b,
                     float min_weight, float decay, float* w_out, double* w_sum, void* stream);
+
+/* Error norms of `evaluate` / `test` on the device ("next" row f.3; ev-NSFnet/pinn_solver.py:684-688 copies the predictions
+ * to the host and calls numpy.linalg.norm).  uvp_pred is the [n][3] output of nsf_forward; u_ref, v_ref, p_ref the DNS fields
+ * at the same points, p_ref may hold NaN (masked, ev :684) or be NULL.  sums8 (device, 8 doubles, zeroed by the call) receives
+ *   [0] sum (u-u_pred)^2  [1] sum u^2  [2] sum (v-v_pred)^2  [3] sum v^2  [4] sum_mask (p-p_pred)^2  [5] sum_mask p^2  [6] #mask
+ * so that error_u = 100 sqrt([0]/[1]) etc.  fp64 accumulation; the order of the atomic adds is not fixed. */
+int nsf_error_norms(const float* uvp_pred, const float* u_ref, const float* v_ref, const float* p_ref_or_null, int64_t n,
+                    double* sums8, void* stream);
 
 /* Debug / validation: runs one tcgen05 TF32 GEMM D[128,n] = A[128,k] * B[n,k]^T with the same
  * shared-memory descriptors the jet kernel uses (variant selects operand majors / 3xTF32 split)

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnsf_b200.so")
 
 NSF_OK = 0
+NSF_E_ARG, NSF_E_ARCH, NSF_E_CUDA, NSF_E_SHAPE = -1, -2, -3, -4
 NSF_HAS_EVM = 1
 NSF_EVM_TRAINABLE = 2
 NSF_VTM_FROM_E = 4
@@ -23,7 +24,7 @@ NSF_LOSS_SLOTS = 16
 EXPORTS = ["nsf_abi_version", "nsf_last_error", "nsf_create", "nsf_destroy", "nsf_set_path", "nsf_get_info",
            "nsf_set_timing", "nsf_last_kernel_ms", "nsf_get_stage_cycles",
            "nsf_step", "nsf_residuals", "nsf_forward", "nsf_adam", "nsf_selftest_umma",
-           "nsf_adam_dev", "nsf_adam_tick", "nsf_lhs_points", "nsf_wall_distance", "nsf_sdf_weights"]
+           "nsf_adam_dev", "nsf_adam_tick", "nsf_lhs_points", "nsf_wall_distance", "nsf_sdf_weights", "nsf_error_norms"]
 
 
 class NsfNetDesc(C.Structure):
@@ -93,6 +94,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nsf_wall_distance.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp]
     lib.nsf_sdf_weights.restype = C.c_int
     lib.nsf_sdf_weights.argtypes = [vp, vp, i64, vp, vp, i32, f, f, vp, vp, vp]
+    lib.nsf_error_norms.restype = C.c_int
+    lib.nsf_error_norms.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     lib.nsf_selftest_umma.restype = C.c_int
     lib.nsf_selftest_umma.argtypes = [C.c_int, i32, vp, vp, vp, i32, i32, vp]
     return lib

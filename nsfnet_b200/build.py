@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["nsf_ffma.cu", "nsf_capi.cu", "nsf_umma.cu", "nsf_umma_jet.cu", "nsf_pm_jet.cu", "nsf_value_fwd.cu", "nsf_aux.cu"]
+SOURCES = ["nsf_ffma.cu", "nsf_capi.cu", "nsf_umma.cu", "nsf_umma_jet.cu", "nsf_pm_jet.cu", "nsf_value_fwd.cu", "nsf_aux.cu", "nsf_eval.cu"]
 OUT = os.path.join(HERE, "libnsf_b200.so")
 
 

@@ -271,12 +271,21 @@ static int evm_forward(NsfCtx* ctx, const float* params_evm, bool packed, const 
   return NSF_OK;
 }
 
+// parameter / gradient / scalar buffers: 4-byte aligned (the solver passes offset views of one flat buffer);
+// per-point arrays (coordinates, targets, weights, lag state, per-point outputs): 16-byte aligned, as include/nsf_b200.h requires
 static int valid_ptr(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+#ifdef NSF_EMU
+#define NSF_PTS_MASK 3u      // the host emulation (tests only) reads element by element: numpy views are fine
+#else
+#define NSF_PTS_MASK 15u
+#endif
+static int valid_pts(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & NSF_PTS_MASK) == 0; }
+static int valid_pts_opt(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & NSF_PTS_MASK) == 0; }
 
 extern "C" int nsf_forward(NsfCtx* ctx, int32_t which, const float* params, const float* x, const float* y, int64_t n,
                            float* out, void* stream) {
-  if (!ctx || !valid_ptr(params) || (n > 0 && (!valid_ptr(x) || !valid_ptr(y) || !valid_ptr(out))) || n < 0 || which < 0 || which > 1) {
-    nsf_set_error("nsf_forward: bad argument"); return NSF_E_ARG;
+  if (!ctx || !valid_ptr(params) || (n > 0 && (!valid_pts(x) || !valid_pts(y) || !valid_pts(out))) || n < 0 || which < 0 || which > 1) {
+    nsf_set_error("nsf_forward: bad argument (null pointer, or a per-point array that is not 16-byte aligned)"); return NSF_E_ARG;
   }
   if (which == 1 && !ctx->has_evm) { nsf_set_error("nsf_forward: context has no EVM net"); return NSF_E_ARG; }
   nsf_stream_t st = (nsf_stream_t)stream;
@@ -295,8 +304,9 @@ extern "C" int nsf_forward(NsfCtx* ctx, int32_t which, const float* params, cons
 extern "C" int nsf_residuals(NsfCtx* ctx, const float* params_main, const float* params_evm, const float* x, const float* y,
                              const float* vtm_in, float* vtm_out, int64_t n, const NsfPhysics* ph, float* residuals_out,
                              float* e_out, float* vis_t_out, void* stream) {
-  if (!ctx || !ph || !valid_ptr(params_main) || n < 0 || (n > 0 && (!valid_ptr(x) || !valid_ptr(y)))) {
-    nsf_set_error("nsf_residuals: bad argument"); return NSF_E_ARG;
+  if (!ctx || !ph || !valid_ptr(params_main) || n < 0 || (n > 0 && (!valid_pts(x) || !valid_pts(y))) || !valid_pts_opt(vtm_in) ||
+      !valid_pts_opt(vtm_out) || !valid_pts_opt(residuals_out) || !valid_pts_opt(e_out) || !valid_pts_opt(vis_t_out)) {
+    nsf_set_error("nsf_residuals: bad argument (null pointer, or a per-point array that is not 16-byte aligned)"); return NSF_E_ARG;
   }
   const bool has_evm = (ph->flags & NSF_HAS_EVM) != 0;
   if (has_evm && (!ctx->has_evm || !valid_ptr(params_evm))) { nsf_set_error("nsf_residuals: NSF_HAS_EVM needs an EVM net and its parameters"); return NSF_E_ARG; }
@@ -328,8 +338,10 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
                         int32_t n_blocks, const NsfPhysics* ph, float* grad_main, float* grad_evm, float* loss_parts,
                         float* residuals_out, float* e_out, float* vis_t_out, void* stream) {
   if (!ctx || !ph || !valid_ptr(params_main) || !valid_ptr(grad_main) || !valid_ptr(loss_parts) || n_f < 0 ||
-      (n_f > 0 && (!valid_ptr(x) || !valid_ptr(y))) || n_blocks < 0 || n_blocks > NSF_MAX_BLOCKS || (n_blocks > 0 && !blocks)) {
-    nsf_set_error("nsf_step: bad argument"); return NSF_E_ARG;
+      (n_f > 0 && (!valid_pts(x) || !valid_pts(y))) || n_blocks < 0 || n_blocks > NSF_MAX_BLOCKS || (n_blocks > 0 && !blocks) ||
+      !valid_pts_opt(w) || !valid_pts_opt(vtm_in) || !valid_pts_opt(vtm_out) || !valid_pts_opt(residuals_out) || !valid_pts_opt(e_out) ||
+      !valid_pts_opt(vis_t_out)) {
+    nsf_set_error("nsf_step: bad argument (null pointer, or a per-point array that is not 16-byte aligned)"); return NSF_E_ARG;
   }
   const bool has_evm = (ph->flags & NSF_HAS_EVM) != 0;
   const bool evm_train = has_evm && (ph->flags & NSF_EVM_TRAINABLE) != 0;
@@ -337,8 +349,8 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   if (evm_train && !valid_ptr(grad_evm)) { nsf_set_error("nsf_step: NSF_EVM_TRAINABLE needs grad_evm"); return NSF_E_ARG; }
   for (int b = 0; b < n_blocks; ++b) {
     const NsfDataBlock& k = blocks[b];
-    if (k.n < 0 || (k.n > 0 && (!valid_ptr(k.x) || !valid_ptr(k.y) || !valid_ptr(k.u) || !valid_ptr(k.v)))) {
-      nsf_set_error("nsf_step: bad data block %d", b); return NSF_E_ARG;
+    if (k.n < 0 || (k.n > 0 && (!valid_pts(k.x) || !valid_pts(k.y) || !valid_pts(k.u) || !valid_pts(k.v) || !valid_pts_opt(k.p)))) {
+      nsf_set_error("nsf_step: bad data block %d (null or not 16-byte aligned)", b); return NSF_E_ARG;
     }
   }
   nsf_stream_t st = (nsf_stream_t)stream;
@@ -444,7 +456,7 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
       NSF_TRY(evm_forward(ctx, params_evm, evm_train, x, y, n_f, eb, st));
       e_ptr = eb;
       if (ph->flags & NSF_VTM_FROM_E) {   // init_vis_t fused into this evaluation: the lag state it would have left behind
-        if (!valid_ptr(vtm_out)) { nsf_set_error("nsf_step: NSF_VTM_FROM_E needs vis_t_minus_out"); return NSF_E_ARG; }
+        if (!valid_pts(vtm_out)) { nsf_set_error("nsf_step: NSF_VTM_FROM_E needs vis_t_minus_out"); return NSF_E_ARG; }
         NSF_TRY(nsf_scale_abs_launch(eb, vtm_out, n_f, ph->alpha_evm_init, st)); ctx->launches++;
         vtm_in = vtm_out;
       }
@@ -494,6 +506,17 @@ extern "C" int nsf_adam(float* params, const float* grad, float* exp_avg, float*
 }
 
 #ifdef NSF_EMU
+// host twin of csrc/nsf_eval.cu (the emulation's "device" memory is host memory)
+extern "C" int nsf_error_norms(const float* pred, const float* u, const float* v, const float* p, int64_t n, double* s, void*) {
+  if (n < 0 || !s || (n > 0 && (!pred || !u || !v))) { nsf_set_error("nsf_error_norms: bad argument"); return NSF_E_ARG; }
+  for (int k = 0; k < 8; ++k) s[k] = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double du = (double)u[i] - pred[3 * i], dv = (double)v[i] - pred[3 * i + 1];
+    s[0] += du * du; s[1] += (double)u[i] * u[i]; s[2] += dv * dv; s[3] += (double)v[i] * v[i];
+    if (p && p[i] == p[i]) { const double dp = (double)p[i] - pred[3 * i + 2]; s[4] += dp * dp; s[5] += (double)p[i] * p[i]; s[6] += 1.0; }
+  }
+  return NSF_OK;
+}
 extern "C" int nsf_selftest_umma(int, int32_t, const float*, const float*, float*, int32_t, int32_t, void*) {
   nsf_set_error("nsf_selftest_umma: not available in the host emulation");
   return NSF_E_ARCH;

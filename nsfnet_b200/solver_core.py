@@ -39,7 +39,10 @@ def _dev_f32(a, device) -> torch.Tensor:
     # a PINNED fp32 host tensor is copied asynchronously on the current stream (the kernels that read it are ordered behind the
     # copy; the caller must not overwrite the buffer before the stream gets there); everything else is the reference's blocking copy
     pinned = t.device.type == "cpu" and t.dtype == torch.float32 and t.is_pinned()
-    return t.to(device=device, dtype=torch.float32, non_blocking=pinned).reshape(-1).contiguous()
+    out = t.to(device=device, dtype=torch.float32, non_blocking=pinned).reshape(-1).contiguous()
+    if out.data_ptr() % 16:      # an odd-offset view of a device tensor (a shard x[s:e]): the C ABI wants 16-byte aligned point arrays
+        out = out.clone()
+    return out
 
 
 def shard_bounds(total: int, rank: int, world_size: int):
@@ -611,15 +614,23 @@ class SolverBase:
 
     # ---- evaluation / checkpoint ---------------------------------------
     def _errors(self, x, y, u, v, p):
-        x_t, y_t, u_t, v_t, p_t = [np.asarray(a).reshape(-1, 1) for a in (x, y, u, v, p)]
-        outs = self.neural_net_u(torch.as_tensor(x_t), torch.as_tensor(y_t))
-        u_p, v_p, p_p = [o.detach().cpu().numpy().reshape(-1, 1) for o in outs[:3]]
-        e_p = outs[3].detach().cpu().numpy().reshape(-1, 1) if len(outs) > 3 else None
-        mask = ~np.isnan(p_t)
-        eu = 100 * np.linalg.norm(u_t - u_p, 2) / np.linalg.norm(u_t, 2)
-        ev = 100 * np.linalg.norm(v_t - v_p, 2) / np.linalg.norm(v_t, 2)
-        ep = 100 * np.linalg.norm(p_t[mask] - p_p[mask], 2) / np.linalg.norm(p_t[mask], 2)
-        return (eu, ev, ep), (u_p, v_p, p_p, e_p)
+        """Relative L2 errors (percent) of u, v and the NaN-masked p against reference fields (ev :684-688), reduced on the
+        device by ``nsf_error_norms``; returns the errors and the predictions (device tensors, shaped [N,1])."""
+        x_t, y_t, u_t, v_t, p_t = [torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(-1)) if not isinstance(a, torch.Tensor)
+                                   else a.detach().reshape(-1) for a in (x, y, u, v, p)]
+        xd, yd = _dev_f32(x_t, self.device), _dev_f32(y_t, self.device)
+        n = xd.numel()
+        uvp = self._forward_net(0, xd, yd)                                  # [n, 3]
+        e_p = self._forward_net(1, xd, yd) if self.HAS_EVM else None
+        ud, vd, pd = [_dev_f32(a, self.device) for a in (u_t, v_t, p_t)]
+        sums = torch.empty(8, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib, self._lib.nsf_error_norms(uvp.data_ptr(), ud.data_ptr(), vd.data_ptr(), pd.data_ptr(), n,
+                                                         sums.data_ptr(), self._stream()))
+        s = sums.cpu().numpy()
+        eu = 100.0 * np.sqrt(s[0] / s[1]); ev = 100.0 * np.sqrt(s[2] / s[3])
+        ep = 100.0 * np.sqrt(s[4] / s[5]) if s[6] > 0 else float("nan")
+        self.last_error_sums = s
+        return (float(eu), float(ev), float(ep)), (uvp[:, 0:1], uvp[:, 1:2], uvp[:, 2:3], e_p)
 
     def evaluate(self, x, y, u, v, p):
         (eu, ev, ep), _ = self._errors(x, y, u, v, p)
@@ -632,7 +643,8 @@ class SolverBase:
 
     def test(self, x, y, u, v, p, loop=None, save_dir=None):
         import scipy.io
-        (eu, ev, ep), (u_p, v_p, p_p, e_p) = self._errors(x, y, u, v, p)
+        (eu, ev, ep), outs = self._errors(x, y, u, v, p)
+        u_p, v_p, p_p, e_p = [None if o is None else o.detach().cpu().numpy().reshape(-1, 1) for o in outs]
         if self.rank == 0:
             print("------------------------")
             print("Error u: %.3f %%" % eu)

@@ -57,9 +57,11 @@ def test_grid_inference_error_norms_and_result_file(tmp_path):
     eu, ev_, ep = P.evaluate(x, y, u_t, v_t, p_t)
     up, vp, pp = [a.double().cpu().numpy().reshape(-1, 1) for a in (u, v, p)]
     m = ~np.isnan(p_t)
-    assert abs(eu - 100 * np.linalg.norm(u_t - up) / np.linalg.norm(u_t)) < 1e-6
-    assert abs(ev_ - 100 * np.linalg.norm(v_t - vp) / np.linalg.norm(v_t)) < 1e-6
-    assert abs(ep - 100 * np.linalg.norm(p_t[m] - pp[m]) / np.linalg.norm(p_t[m])) < 1e-6
+    # (the norms are reduced on the device in fp64 from the fp32-rounded reference fields: 1e-5 percentage points of the host formula)
+    assert abs(eu - 100 * np.linalg.norm(u_t - up) / np.linalg.norm(u_t)) < 1e-4
+    assert abs(ev_ - 100 * np.linalg.norm(v_t - vp) / np.linalg.norm(v_t)) < 1e-4
+    assert abs(ep - 100 * np.linalg.norm(p_t[m] - pp[m]) / np.linalg.norm(p_t[m])) < 1e-4
+    assert P.last_error_sums[6] == m.sum()
     assert abs(eu - 100 * 0.01 / 1.01) < 1e-3
     P.test(x, y, u_t, v_t, p_t, loop=7, save_dir=str(tmp_path))
     d = scipy.io.loadmat(os.path.join(str(tmp_path), "cavity_result_loop_7.mat"))
@@ -109,3 +111,62 @@ def test_reference_checkpoint_files_and_full_state_resume(tmp_path):
         more(B)
         assert torch.equal(A.net.flat_params(), B.net.flat_params()), fused
         assert torch.equal(A.vis_t_minus, B.vis_t_minus)
+
+
+DNS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dns")
+
+
+@pytest.mark.parametrize("fname,side,n_nan", [("cavity_Re4000_384_Uniform.mat", 385, 237), ("cavity_Re2000_256.mat", 257, 151)])
+def test_evaluate_on_the_reference_dns_files(fname, side, n_nan):
+    """BASELINE config 4: the reference's own DNS fixtures (cavity_Re4000_384_Uniform.mat: 385 x 385 = 148 225 points, 237 of them
+    with NaN pressure; NSFnet/data/cavity_Re2000_256.mat), loaded through DataLoader.loading_evaluate_data (ev-NSFnet/
+    cavity_data.py:144-160) and scored by evaluate() (ev :669-693) with the error norms reduced on the device; the truth is
+    the reference's formula (ev :684-688) applied to an fp64 forward of the same weights."""
+    import torch
+    from nsfnet_b200.cavity_data import DataLoader
+    P = _solver()
+    x, y, u, v, p = DataLoader(N_f=2000).loading_evaluate_data(os.path.join(DNS, fname))
+    assert x.shape == (side * side, 1) and int(np.isnan(p).sum()) == n_nan
+    eu, ev_, ep = P.evaluate(x, y, u, v, p)
+    assert P.last_error_sums[6] == side * side - n_nan
+    with torch.no_grad():
+        xy = torch.as_tensor(np.hstack([x, y]), dtype=torch.float64, device="cuda")
+        ref = P.net.double()(xy).cpu().numpy()
+        P.net.float(); P.net.flatten_()
+    m = ~np.isnan(p)
+    tu = 100 * np.linalg.norm(u - ref[:, 0:1]) / np.linalg.norm(u)
+    tv = 100 * np.linalg.norm(v - ref[:, 1:2]) / np.linalg.norm(v)
+    tp = 100 * np.linalg.norm(p[m] - ref[:, 2:3][m]) / np.linalg.norm(p[m])
+    for got, want in ((eu, tu), (ev_, tv), (ep, tp)):
+        assert abs(got - want) <= 1e-5 * want, (got, want)
+    # test() writes the reference's result file for the 385 x 385 grid too (the reference hard-codes 257 x 257, ev :723-726)
+    import tempfile
+    import scipy.io
+    with tempfile.TemporaryDirectory() as d:
+        P.test(x, y, u, v, p, loop=1, save_dir=d)
+        r = scipy.io.loadmat(os.path.join(d, "cavity_result_loop_1.mat"))
+        assert r["U_pred"].shape == (side, side) and abs(float(np.asarray(r["error_u"]).reshape(-1)[0]) - eu) < 1e-9
+
+
+def test_short_training_reduces_the_dns_error():
+    """A few thousand fused iterations of ev-NSFnet at Re = 2000 on the device point layer: the velocity error against the
+    reference's DNS field (NSFnet/data/cavity_Re2000_256.mat) must fall well below the untrained net's.  The long regression
+    (scripts/train_dns_regression.py, numbers in profiles/r2_dns_regression.txt) runs the staged schedule."""
+    import torch
+    from nsfnet_b200.cavity_data import DataLoader, DeviceDataLoader
+    from nsfnet_b200.ev_nsfnet import PysicsInformedNeuralNetwork
+    torch.manual_seed(0)
+    P = PysicsInformedNeuralNetwork(Re=2000, layers=6, hidden_size=80, layers_1=4, hidden_size_1=40, N_f=20000, alpha_evm=0.05,
+                                    bc_weight=10, eq_weight=1, supervised_data_weight=0.0)
+    P.log_interval = 10 ** 9; P.checkpoints = False; P.verbose = False
+    dl = DeviceDataLoader(P.device, N_f=20000, sort_training_points=False, seed=0)
+    P.set_boundary_data(dl.loading_boundary_data())
+    P.set_eq_training_shard(dl.loading_training_data())
+    x, y, u, v, p = DataLoader(N_f=1).loading_evaluate_data(os.path.join(DNS, "cavity_Re2000_256.mat"))
+    e0 = P.evaluate(x, y, u, v, p)
+    P.enable_fused_step(True)
+    P.train(num_epoch=3000, lr=1e-3)
+    e1 = P.evaluate(x, y, u, v, p)
+    print("DNS error (u, v, p) untrained", e0, "after 3000 iterations", e1)
+    assert np.isfinite(e1).all()
+    assert e1[0] < 0.95 * e0[0] and e1[1] < 0.9 * e0[1] and e1[2] < 0.6 * e0[2]      # measured: 102 -> 88 %, 124 -> 98 %, 385 -> 147 %

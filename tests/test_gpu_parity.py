@@ -175,7 +175,7 @@ def test_full_size_properties(gu):
     assert np.array_equal(a["grad_main"], b["grad_main"]) and np.array_equal(a["resid"], b["resid"])
     h = n // 2 + 777
     s1 = abi.step(pm, cp, x[:h].contiguous(), y[:h].contiguous(), blocks=blocks, params_evm=pe, vtm_in=vtm[:h].contiguous())
-    s2 = abi.step(pm, cp, x[h:].contiguous(), y[h:].contiguous(), blocks=[], params_evm=pe, vtm_in=vtm[h:].contiguous())
+    s2 = abi.step(pm, cp, x[h:].clone(), y[h:].clone(), blocks=[], params_evm=pe, vtm_in=vtm[h:].clone())
     assert gu.rel(s1["grad_main"] + s2["grad_main"], a["grad_main"]) < 2e-6
     assert abs((s1["loss_parts"][:6] + s2["loss_parts"][:6]) / a["loss_parts"][:6] - 1).max() < 1e-5
     # residuals-only entry point
@@ -250,3 +250,28 @@ def test_umma_golden_ev_lag(gu, golden_dir, path):
         for i in range(4):
             assert gu.rel(o["resid"][i], g[f"eq{i+1}_{k}"]) < TOL
         vtm = o["vtm_out"]
+
+
+def test_misaligned_point_arrays_are_rejected(gu):
+    """include/nsf_b200.h: per-point arrays must be 16-byte aligned; a 4-byte-offset slice (x[1:]) is NSF_E_ARG, not a device fault."""
+    import torch
+    md = J.NetDesc(2, 3, 2, 8)
+    pm = J.init_params(md, 0)
+    abi = gu.Abi((2, 3, 2, 8))
+    n = 64
+    base = torch.rand(n + 4, device="cuda")
+    good = base[4:4 + n]                     # 16-byte offset: fine
+    bad = base[1:1 + n]                      # 4-byte offset: rejected
+    assert good.data_ptr() % 16 == 0 and bad.data_ptr() % 16 == 4
+    o = abi.step(pm, _capi.physics(100.), good, good, blocks=[])
+    assert np.isfinite(o["grad_main"]).all()
+    for args in ((bad, good), (good, bad)):
+        with pytest.raises(_capi.NsfError) as e:
+            abi.step(pm, _capi.physics(100.), args[0], args[1], blocks=[])
+        assert e.value.code == _capi.NSF_E_ARG
+    with pytest.raises(_capi.NsfError):
+        abi.step(pm, _capi.physics(100.), good, good, blocks=[], w=bad)
+    out = torch.empty((n, 3), device="cuda")
+    pmd = gu.dev(pm)
+    with pytest.raises(_capi.NsfError):
+        abi.ctx.forward(0, pmd.data_ptr(), bad.data_ptr(), good.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,166 @@
+"""Parity at TRAINED weights, judged against an fp64 run of the reference graph (SURVEY 7 hard part 3, 8c).
+
+After a few thousand Adam steps the residuals are small sums of large cancelling terms (max |u_xx| ~ 40, residual rms ~ 3e-2)
+and the gradient is a sum of cancelling per-point terms: the reference's OWN fp32 autograd path is then 1e-6 .. 1.4e-5 (rel-L2)
+away from the same graph evaluated in fp64, so two fp32 evaluation orders cannot be asked to agree to 1e-5 with each other.
+tests/golden/trained_*.npz (tests/golden/make_golden_r2.py) hold, for the state the UNMODIFIED reference reached after 3000 / 2000
+Adam steps (N_f = 4000, 516 boundary points), the reference's fp32 outputs and its fp64 outputs on the same fp32-valued inputs.
+The bar for every kernel path:   err(kernel, fp64) <= max(1e-5, 2 * err(reference fp32, fp64))
+for residuals, loss and gradient (norm-wise), plus a floored element-wise check.  The measured triples go to
+gpurun_out/r2_parity_trained.txt (committed as profiles/r2_parity_trained.txt).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from nsfnet_b200 import _capi
+from oracle import jet_numpy as J
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH_NAME = {1: "ffma", 2: "tcgen05 neurons-on-M", 3: "tcgen05 points-on-M"}
+
+
+def _bar(err_kernel, err_ref):
+    return err_kernel <= max(1e-5, 2.0 * err_ref)
+
+
+def _elem(a, truth):
+    """worst element error relative to |truth| floored at 1 % of the tensor's rms"""
+    a = np.asarray(a, np.float64).ravel(); t = np.asarray(truth, np.float64).ravel()
+    floor = 0.01 * np.sqrt(np.mean(t * t))
+    return float(np.max(np.abs(a - t) / (np.abs(t) + floor)))
+
+
+def _report(lines):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r2_parity_trained.txt"), "a") as f:
+        f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+def _check(name, path, o, g, n_eq, n, nb):
+    from tests import gpu_util as gu
+    lines = [f"{name}  path {path} ({PATH_NAME[path]}):   kernel-vs-fp64 | reference-fp32-vs-fp64 | bar = max(1e-5, 2 x reference)"]
+    ok = True
+    kg, rg = gu.rel(o["grad_main"], g["grad_f64"]), gu.rel(g["grad_f32"], g["grad_f64"])
+    lines.append(f"  gradient rel-L2      {kg:.3e} | {rg:.3e} | {max(1e-5, 2 * rg):.3e}")
+    ok &= _bar(kg, rg)
+    ke, re_ = _elem(o["grad_main"], g["grad_f64"]), _elem(g["grad_f32"], g["grad_f64"])
+    lines.append(f"  gradient worst elem  {ke:.3e} | {re_:.3e} | {max(1e-4, 2 * re_):.3e}   (relative to |truth| + 1 % rms)")
+    ok &= ke <= max(1e-4, 2.0 * re_)
+    for i in range(n_eq):
+        kr, rr = gu.rel(o["resid"][i], g[f"eq{i+1}_f64"]), gu.rel(g[f"eq{i+1}_f32"], g[f"eq{i+1}_f64"])
+        lines.append(f"  eq{i+1} residual rel-L2 {kr:.3e} | {rr:.3e} | {max(1e-5, 2 * rr):.3e}")
+        ok &= _bar(kr, rr)
+    lp = o["loss_parts"]
+    w4 = 0.1 * lp[3] if n_eq == 4 else 0.0
+    loss = 10.0 * (lp[6] + lp[7]) / nb + (lp[0] + lp[1] + lp[2] + w4) / n
+    kl = abs(loss - float(g["loss_f64"])) / float(g["loss_f64"]); rl = abs(float(g["loss_f32"]) - float(g["loss_f64"])) / float(g["loss_f64"])
+    lines.append(f"  loss                 {kl:.3e} | {rl:.3e} | {max(1e-5, 2 * rl):.3e}")
+    ok &= _bar(kl, rl)
+    _report(lines)
+    return ok
+
+
+@pytest.mark.parametrize("name,path", [("trained_ns_re100", 3), ("trained_ns_re1000", 3), ("trained_ns_re100", 1), ("trained_ns_re1000", 1)])
+def test_trained_ns(golden_dir, name, path):
+    from tests import gpu_util as gu
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb, n = xb.size, g["xf"].size
+    abi = gu.Abi((2, 3, 4, 120), path=path)
+    o = abi.step(g["params"], _capi.physics(float(g["Re"])), g["xf"], g["yf"], blocks=[(xb, yb, ub, vb, None, 10. / nb, 10. / nb, 0.)])
+    assert o["info"]["path"] == path
+    assert _check(name, path, o, g, 3, n, nb)
+
+
+@pytest.mark.parametrize("path", [3, 2, 1])
+def test_trained_ev(golden_dir, path):
+    from tests import gpu_util as gu
+    g = np.load(os.path.join(golden_dir, "trained_ev_re2000.npz"))
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb, n = xb.size, g["xf"].size
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40), path=path)
+    cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
+    o = abi.step(g["params_main"], cp, g["xf"], g["yf"], blocks=[(xb, yb, ub, vb, None, 10. / nb, 10. / nb, 0.)],
+                 params_evm=g["params_evm"], vtm_in=g["vis_t_minus"])
+    assert o["info"]["path"] == path
+    assert _check("trained_ev_re2000", path, o, g, 4, n, nb)
+    assert gu.rel(o["e"], g["e_f64"]) <= max(1e-5, 2 * gu.rel(g["e_f32"], g["e_f64"]))
+
+
+@pytest.mark.parametrize("path", [3, 2])
+def test_golden_shipped_boundary_set_and_sdf_weights(golden_dir, path):
+    """N_b = 2052: the boundary points come from the reference's own DataLoader.loading_boundary_data(), the SDF weights from
+    its cKDTree over them (ev-NSFnet/cavity_data.py:47-94,118-130); production.yaml's nets, 20 000 collocation points."""
+    from tests import gpu_util as gu
+    from nsfnet_b200.cavity_data import cavity_boundary
+    g = np.load(os.path.join(golden_dir, "ev_re5000_nb2052_sdf.npz"))
+    nb, n = g["xb"].size, g["xf"].size
+    assert nb == 2052
+    mine = cavity_boundary(513)                      # the package's own boundary set is the reference's, bit for bit in fp32
+    for a, b in zip(mine, (g["xb"], g["yb"], g["ub"], g["vb"])):
+        assert np.array_equal(np.asarray(a, np.float32).reshape(-1), b)
+    abi = gu.Abi((2, 3, 6, 80), (2, 1, 4, 40), path=path)
+    cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
+    o = abi.step(g["params_main"], cp, g["xf"], g["yf"], blocks=[(g["xb"], g["yb"], g["ub"], g["vb"], None, 10. / nb, 10. / nb, 0.)],
+                 params_evm=g["params_evm"], w=g["w"], vtm_in=g["vis_t_minus"])
+    assert gu.rel(o["grad_main"], g["grad_f32"]) < 1e-5
+    for i in range(4):
+        assert gu.rel(o["resid"][i], g[f"eq{i+1}_f32"]) < 1e-5
+    lp = o["loss_parts"]
+    loss = 10.0 * (lp[6] + lp[7]) / nb + (lp[0] + lp[1] + lp[2] + 0.1 * lp[3]) / n
+    assert abs(loss - float(g["loss_f32"])) < 1e-5 * float(g["loss_f32"])
+    for i in range(4):
+        assert abs(lp[i] / n - g["loss_eq_f32"][i]) < 1e-5 * g["loss_eq_f32"][i]
+
+
+@pytest.mark.parametrize("name", ["curve_full_ns_re100", "curve_full_ns_re1000"])
+def test_full_size_curves_track_reference(golden_dir, name):
+    """BASELINE config 1 at full size: NSFnet 4x120, N_f = 10 000, the reference's 2052 boundary points, Adam
+    lr 1e-3, 5000 steps, loss every 100 steps -- recorded from the reference's own loop body (NSFnet/pinn_solver.py:250-254)
+    on CPU, with the same loop in fp64 as the rounding envelope.  Bound: err_k <= max(2e-5, 2 x envelope_k) with the envelope
+    accumulated up to step k.  Adam at lr 1e-3 turns rounding differences into loss spikes late in the run (the reference's own
+    fp32 curve is up to 5x away from its fp64 twin at single samples), so the level of the last 1000 steps is checked too."""
+    import torch
+    from nsfnet_b200.nsfnet import PysicsInformedNeuralNetwork
+    from nsfnet_b200.cavity_data import cavity_boundary
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    P = PysicsInformedNeuralNetwork(Re=float(g["Re"]), layers=4, hidden_size=120, N_f=g["xf"].size, bc_weight=10, eq_weight=1)
+    off = 0
+    flat = torch.as_tensor(g["params"]).cuda()
+    with torch.no_grad():
+        for p in P.net.parameters():
+            p.copy_(flat[off:off + p.numel()].view(p.shape)); off += p.numel()
+    P.verbose = False
+    P.set_boundary_data(cavity_boundary(513)); P.set_eq_training_data((g["xf"], g["yf"]))
+    P.opt.param_groups[0]["lr"] = float(g["lr"])
+    every = int(g["every"])
+    curve = []
+    for k in range(int(g["steps"])):
+        loss, _ = P.fwd_computing_loss_2d()
+        loss.backward(); P.opt.step(); P.opt.zero_grad()
+        if k % every == 0:
+            curve.append(loss.detach())
+    curve = torch.stack(curve).double().cpu().numpy()
+    ref, c64 = g["curve"], g["curve_fp64"]
+    err = np.abs(curve - ref) / ref
+    env = np.maximum.accumulate(np.abs(c64 - ref) / ref)
+    tail = slice(-10, None)
+    lvl, lvl_ref, lvl64 = np.median(curve[tail]), np.median(ref[tail]), np.median(c64[tail])
+    lines = [f"{name}: {int(g['steps'])} Adam steps, N_f = {g['xf'].size}, sampled every {every}",
+             f"  max deviation from the reference curve  {err.max():.3e} (at sample {int(err.argmax())}); reference's own fp32-vs-fp64 envelope {env.max():.3e}",
+             f"  first 10 samples: deviation {np.array2string(err[:10], precision=2)}",
+             f"                    envelope  {np.array2string(env[:10], precision=2)}",
+             f"  median loss of the last 1000 steps: kernel {lvl:.4e}, reference fp32 {lvl_ref:.4e}, reference fp64 {lvl64:.4e}"]
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r2_curves.txt"), "a") as f:
+        f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+    assert err[0] < 1e-5
+    assert np.all(err <= np.maximum(2e-5, 2.0 * env)), (err, env)
+    assert abs(np.log(lvl / lvl_ref)) <= max(np.log(1.25), 2 * abs(np.log(lvl64 / lvl_ref)))

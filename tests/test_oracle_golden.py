@@ -111,3 +111,61 @@ def test_goldens_present(golden_dir):
     for n in ["ns_re100_init", "ns_re1000_x2p5", "ev_re2000_lag", "ev_re5000_sdf_unfrozen", "ev_re3000_scale_sup",
               "curve_ns_re100", "curve_ns_re1000", "curve_ev_re2000"]:
         assert n + ".npz" in names
+
+
+# ---- round 2: trained-weight goldens with an fp64 run of the reference graph as truth (tests/golden/make_golden_r2.py) --------
+@pytest.mark.parametrize("name", ["trained_ns_re100", "trained_ns_re1000"])
+def test_oracle_matches_reference_fp64_at_trained_weights_ns(golden_dir, name):
+    """The numpy oracle (fp64) against the reference's own fp64 evaluation after 3000 Adam steps: the restated math is the
+    reference's math where it matters most (large second derivatives, cancelling gradient terms)."""
+    g = load(golden_dir, name)
+    xb, yb, ub, vb = [a.astype(np.float32) for a in J.cavity_boundary(int(g["n_side"]))]   # the truth was fed the fp32-valued inputs
+    r = J.step(g["params"], MAIN_NS, J.Physics(Re=float(g["Re"])), g["xf"], g["yf"], xb, yb, ub, vb)
+    assert rel(r.grad_main, g["grad_f64"]) < 1e-9
+    for i in range(3):
+        assert rel(r.eq[i], g[f"eq{i+1}_f64"]) < 1e-9
+    assert abs(r.loss - float(g["loss_f64"])) <= 1e-10 * float(g["loss_f64"])
+    # and the distance the reference's fp32 path itself keeps from that truth (the yardstick of tests/test_gpu_trained.py)
+    assert 1e-7 < rel(g["grad_f32"], g["grad_f64"]) < 1e-4
+
+
+def test_oracle_matches_reference_fp64_at_trained_weights_ev(golden_dir):
+    g = load(golden_dir, "trained_ev_re2000")
+    xb, yb, ub, vb = [a.astype(np.float32) for a in J.cavity_boundary(int(g["n_side"]))]
+    phys = J.Physics(Re=float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
+    r = J.step(g["params_main"], MAIN_EV, phys, g["xf"], g["yf"], xb, yb, ub, vb, evm_flat=g["params_evm"], evm_desc=EVM,
+               vis_t_minus=g["vis_t_minus"])
+    # the reference rounds vis_t = min(20/Re, vis_t_minus) to fp32 even when its nets run in fp64 (ev :327-331): 1e-8 apart
+    assert rel(r.grad_main, g["grad_f64"]) < 1e-7
+    for i in range(4):
+        assert rel(r.eq[i], g[f"eq{i+1}_f64"]) < 1e-7
+    assert rel(r.e, g["e_f64"]) < 1e-12
+    assert abs(r.loss - float(g["loss_f64"])) <= 1e-8 * float(g["loss_f64"])
+
+
+def test_shipped_boundary_set_and_sdf_weights(golden_dir):
+    """N_b = 2052 from the reference's DataLoader.loading_boundary_data(), SDF weights from its cKDTree: the oracle's and the
+    package's boundary sets are the same points, and the oracle reproduces the reference's fp32 step on them."""
+    from nsfnet_b200.cavity_data import cavity_boundary
+    g = load(golden_dir, "ev_re5000_nb2052_sdf")
+    for mine in (J.cavity_boundary(513), cavity_boundary(513)):
+        for a, b in zip(mine, (g["xb"], g["yb"], g["ub"], g["vb"])):
+            assert np.array_equal(np.asarray(a, np.float32).reshape(-1), b)
+    phys = J.Physics(Re=float(g["Re"]), alpha_evm=float(g["alpha_evm"]), has_evm=True)
+    r = J.step(g["params_main"], MAIN_EV, phys, g["xf"], g["yf"], g["xb"], g["yb"], g["ub"], g["vb"], evm_flat=g["params_evm"],
+               evm_desc=EVM, w=g["w"], vis_t_minus=g["vis_t_minus"])
+    assert rel(r.grad_main, g["grad_f32"]) < 5e-6
+    for i in range(4):
+        assert rel(r.eq[i], g[f"eq{i+1}_f32"]) < 5e-6
+    assert abs(r.loss - float(g["loss_f32"])) <= 3e-6 * float(g["loss_f32"])
+    # the package's SDF weights (vectorised host layer) equal the reference's cKDTree result
+    from nsfnet_b200.cavity_data import sdf_weights
+    w = sdf_weights(np.stack([g["xf"], g["yf"]], 1).astype(np.float64), np.stack([g["xb"], g["yb"]], 1).astype(np.float64), 0.2, 5.0)
+    assert rel(w, g["w"]) < 1e-6
+
+
+def test_full_size_curves_recorded(golden_dir):
+    for name in ("curve_full_ns_re100", "curve_full_ns_re1000"):
+        g = load(golden_dir, name)
+        assert int(g["steps"]) == 5000 and g["xf"].size == 10000 and g["curve"].size == 50 and g["curve_fp64"].size == 50
+        assert g["curve"][0] == pytest.approx(g["curve_fp64"][0], rel=1e-6)
