@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the 120 000-point Adam-iteration measurement")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 with the neurons on M (round 1), 3 tcgen05 with the points on M")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 FFMA, 3 tcgen05 (points on M)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

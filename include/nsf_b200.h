@@ -109,11 +109,11 @@ int nsf_create(int device, const NsfNetDesc* main_net, const NsfNetDesc* evm_or_
 int nsf_destroy(NsfCtx* ctx);
 
 /* Select the kernel family of the hidden-layer contractions: 0 = auto (the tcgen05 kernel that covers the shape, else FFMA),
- * 1 = force the FP32 FFMA kernels, 2 = tcgen05 3xTF32 kernel with the neurons on the MMA's M (round 1; hidden = 80, 2..6
- * hidden layers), 3 = tcgen05 3xTF32 kernel with the points on M (hidden = 80 with 2..6 hidden layers: the ev-NSFnet main net;
- * hidden = 120 with 2..4: NSFnet); 2 / 3 return NSF_E_SHAPE if the shape is not covered. */
+ * 1 = force the FP32 FFMA kernels, 3 = tcgen05 3xTF32 kernel with the points on the MMA's M (hidden = 80 with 2..6 hidden layers:
+ * the ev-NSFnet main net; hidden = 120 with 2..4: NSFnet); 3 returns NSF_E_SHAPE if the shape is not covered.  (2 was the round-1
+ * tcgen05 kernel, removed: NSF_E_ARG.) */
 int nsf_set_path(NsfCtx* ctx, int path);
-/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 2, 3 tcgen05),
+/* info[0]=SM count, [1]=path that the next nsf_step will use (1 FFMA / 3 tcgen05),
  * [2]=kernel launches issued by the last nsf_* call, [3]=workspace bytes. */
 int nsf_get_info(NsfCtx* ctx, int64_t info[4]);
 
@@ -125,7 +125,7 @@ int nsf_last_kernel_ms(NsfCtx* ctx, float* ms);
 
 /* Diagnostics of the tcgen05 kernel: out == NULL switches per-warp cycle counters on for the following launches;
  * out != NULL (double[256]) synchronises the device and returns the counters of the last launch averaged over CTAs
- * (layout documented at nsf_pm_stage_cycles in csrc/nsf_pm_jet.cu resp. nsf_umma_stage_cycles in csrc/nsf_umma_jet.cu).  Adds clock reads to the kernel: not for
+ * (layout documented at nsf_pm_stage_cycles in csrc/nsf_pm_jet.cu).  Adds clock reads to the kernel: not for
  * timed runs. */
 int nsf_get_stage_cycles(NsfCtx* ctx, double* out);
 

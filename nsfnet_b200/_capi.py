@@ -108,10 +108,11 @@ def load() -> C.CDLL:
     """Open the CUDA library.  Fails loudly when it is missing -- there is nothing to fall back to."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is not built; run __graft_entry__.build() (nvcc, sm_100a). "
+        path = os.environ.get("NSF_B200_LIB", LIB_PATH)      # kernel experiments: another build of the same library
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is not built; run __graft_entry__.build() (nvcc, sm_100a). "
                               "nsfnet_b200 has no CPU or PyTorch fallback for the hot path.")
-        _lib = bind(C.CDLL(LIB_PATH))
+        _lib = bind(C.CDLL(path))
         if _lib.nsf_abi_version() != 1:
             raise ImportError("libnsf_b200.so ABI version mismatch")
     return _lib

@@ -48,7 +48,7 @@ static int init_net(NsfCtx* ctx, NsfNetState& s, const NsfNetDesc* d, bool jet) 
   const NsfNetGeom& g = s.g;
   int occ1 = nsf_ffma_occupancy(1, g.HP), occ4 = jet ? nsf_ffma_occupancy(4, g.HP) : 0;
   if (occ1 <= 0 || (jet && occ4 <= 0)) { nsf_set_error("FFMA kernel does not fit on the SM for hidden=%d", d->hidden); return NSF_E_SHAPE; }
-  s.rows = ctx->sms * (occ1 > occ4 ? occ1 : occ4);
+  s.rows = ctx->sms * (occ1 > occ4 ? occ1 : occ4) + (jet ? ctx->sms : 0);   // + one row per SM: the data blocks' rows behind a persistent tcgen05 launch
   long long st1 = (long long)g.L * g.HP * nsf_ffma_pt(1, g.HP);
   long long st4 = jet ? (long long)g.L * 4 * g.HP * nsf_ffma_pt(4, g.HP) : 0;
   s.stash_stride = st1 > st4 ? st1 : st4;
@@ -106,7 +106,6 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   free_net(ctx->main); free_net(ctx->evm);
   nsf_rt_free(ctx->e_buf); nsf_rt_free(ctx->ebar_buf);
 #ifndef NSF_EMU
-  nsf_umma_free(ctx);
   nsf_pm_free(ctx);
   if (ctx->side) cudaStreamDestroy((cudaStream_t)ctx->side);
   if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
@@ -118,28 +117,22 @@ extern "C" int nsf_destroy(NsfCtx* ctx) {
   return NSF_OK;
 }
 
-// kernel family the next collocation launch uses: 1 = FFMA, 2 = tcgen05 with the neurons on M (round 1, hidden = 80 only),
-// 3 = tcgen05 with the points on M (hidden = 80 and hidden = 120).  Auto (0) prefers 3, then 2, then 1.
+// kernel family the next collocation launch uses: 1 = FFMA, 3 = tcgen05 with the points on M (hidden = 80 and hidden = 120).
+// Auto (0) prefers 3.  (2 was the round-1 tcgen05 kernel with the neurons on M: slower and further from fp64 at trained weights, removed.)
 static int effective_path(const NsfCtx* ctx) {
 #ifdef NSF_EMU
   return 1;
 #else
   if (ctx->path == 1) return 1;
-  if (ctx->path == 2) return nsf_umma_supported(ctx->main.g) ? 2 : 1;
-  if (nsf_pm_supported(ctx->main.g)) return 3;
-  return nsf_umma_supported(ctx->main.g) ? 2 : 1;
+  return nsf_pm_supported(ctx->main.g) ? 3 : 1;
 #endif
 }
 
 extern "C" int nsf_set_path(NsfCtx* ctx, int path) {
-  if (!ctx || path < 0 || path > 3) { nsf_set_error("nsf_set_path: bad argument"); return NSF_E_ARG; }
+  if (!ctx || path < 0 || path > 3 || path == 2) { nsf_set_error("nsf_set_path: path must be 0 (auto), 1 (FFMA) or 3 (tcgen05)"); return NSF_E_ARG; }
 #ifdef NSF_EMU
   if (path >= 2) { nsf_set_error("tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE; }
 #else
-  if (path == 2 && !nsf_umma_supported(ctx->main.g)) {
-    nsf_set_error("tcgen05 path 2 covers hidden = 80 with 2..6 hidden layers; this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
-    return NSF_E_SHAPE;
-  }
   if (path == 3 && !nsf_pm_supported(ctx->main.g)) {
     nsf_set_error("tcgen05 path 3 covers hidden = 80 (2..6 hidden layers) and hidden = 120 (2..4); this net is %d x %d", ctx->main.g.L, ctx->main.g.H);
     return NSF_E_SHAPE;
@@ -161,7 +154,6 @@ extern "C" int nsf_get_stage_cycles(NsfCtx* ctx, double* out) {
   (void)out; nsf_set_error("nsf_get_stage_cycles: tcgen05 path does not exist in the host emulation"); return NSF_E_SHAPE;
 #else
   if (effective_path(ctx) == 3) return nsf_pm_stage_cycles(ctx, out);
-  if (effective_path(ctx) == 2) return nsf_umma_stage_cycles(ctx, out);
   nsf_set_error("nsf_get_stage_cycles: the tcgen05 paths do not cover this net"); return NSF_E_SHAPE;
 #endif
 }
@@ -169,10 +161,6 @@ extern "C" int nsf_get_stage_cycles(NsfCtx* ctx, double* out) {
 // the collocation jet launch (step or residuals) on whichever kernel family is selected
 static int launch_jet(NsfCtx* ctx, NsfKernelArgs& a, const float* flat_main, int* grid, nsf_stream_t st) {
 #ifndef NSF_EMU
-  if (effective_path(ctx) == 2) {
-    NSF_TRY(nsf_umma_init(ctx));
-    return nsf_umma_launch(ctx, a, flat_main, grid, st, &ctx->launches);
-  }
   if (effective_path(ctx) == 3) {
     NSF_TRY(nsf_pm_init(ctx));
     return nsf_pm_launch(ctx, a, flat_main, grid, st, &ctx->launches);
@@ -367,13 +355,12 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     NSF_TRY(nsf_pm_init(ctx));
     grids[0] = nsf_pm_grid(ctx, n_f);
   }
-  if (n_f > 0 && effective_path(ctx) == 2) {   // one persistent CTA per SM, a pair of 8-point tiles per iteration
-    NSF_TRY(nsf_umma_init(ctx));
-    const long long groups = (n_f + nsf_umma_group_points() - 1) / nsf_umma_group_points();
-    grids[0] = (int)(groups < ctx->sms ? groups : ctx->sms);
-  }
 #endif
   for (int b = 0; b < n_blocks; ++b) grids[1 + b] = blocks[b].n > 0 ? grid_for(ctx, M, 1, blocks[b].n) : 0;
+#ifndef NSF_EMU
+  if (n_f > 0 && effective_path(ctx) >= 2)     // the tcgen05 kernels keep their rows to themselves (own layout of the hidden-layer blocks)
+    for (int b = 0; b < n_blocks; ++b) if (grids[1 + b] > M.rows - grids[0]) grids[1 + b] = M.rows - grids[0];
+#endif
   // With the tcgen05 jet kernel (own activation stash, one gradient row per SM) the data blocks get the gradient rows
   // BEHIND the jet kernel's and run on a side stream beside the EVM forward and the jet kernel; otherwise every launch
   // accumulates into the same rows, in stream order.
@@ -476,7 +463,13 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     NSF_TRY(time_mark(ctx, 1, st));
   }
   if (!side) { NSF_TRY(launch_blocks(st)); }
-  NSF_TRY(nsf_finalize_launch(M.g, M.scratch, rows_used, M.map, grad_main, loss_parts, st)); ctx->launches++;
+  {
+    const int* map0 = nullptr;
+#ifndef NSF_EMU
+    if (n_f > 0 && effective_path(ctx) == 3) map0 = nsf_pm_map(ctx);
+#endif
+    NSF_TRY(nsf_finalize_launch(M.g, M.scratch, rows_used, M.map, grad_main, loss_parts, st, map0, grids[0])); ctx->launches++;
+  }
 
   if (evm_train) {
     NsfNetState& E = ctx->evm;

@@ -70,9 +70,10 @@ int nsf_pack_launch(const NsfNetGeom& g, const float* flat, float* pk, nsf_strea
 }
 
 // grad[i] = sum over rows of scratch[row][map[i]] (fp64 accumulation, fixed order => bitwise
-// reproducible); loss_parts[s] likewise.
+// reproducible); loss_parts[s] likewise.  Rows [0, split) may use another layout of the row (map0: the
+// tcgen05 kernel writes its hidden-layer weight gradients in the order it drains tensor memory).
 __global__ void nsf_finalize_kernel(NsfNetGeom g, const float* __restrict__ scratch, int rows, const int* __restrict__ map,
-                                    float* __restrict__ grad, float* __restrict__ loss_parts) {
+                                    float* __restrict__ grad, float* __restrict__ loss_parts, const int* __restrict__ map0, int split) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.n_params;
   if (i >= np + NSF_LOSS_SLOTS) return;
@@ -81,8 +82,19 @@ __global__ void nsf_finalize_kernel(NsfNetGeom g, const float* __restrict__ scra
   const int col = is_loss ? g.gs_loss() + (i - np) : map[i];
   const long long stride = g.gs_row();
   double acc = 0.0;
-  const float* src = scratch + col;
   int r = 0;
+  if (split > 0) {
+    const float* src0 = scratch + (is_loss ? col : map0[i]);
+    for (; r + 8 <= split; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(src0 + (long long)(r + k) * stride);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += (double)v[k];
+    }
+    for (; r < split; ++r) acc += (double)__ldcg(src0 + (long long)r * stride);
+  }
+  const float* src = scratch + col;
   for (; r + 8 <= rows; r += 8) {          // eight independent loads in flight, summed in row order (fixed => bitwise reproducible)
     float v[8];
 #pragma unroll
@@ -96,9 +108,11 @@ __global__ void nsf_finalize_kernel(NsfNetGeom g, const float* __restrict__ scra
 }
 
 int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, const int* map, float* grad,
-                        float* loss_parts, nsf_stream_t st) {
+                        float* loss_parts, nsf_stream_t st, const int* map0, int split) {
   const int n = g.n_params + NSF_LOSS_SLOTS;
-  nsf_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(g, scratch, rows, map, grad, loss_parts);
+  if (!map0 || split < 0) split = 0;
+  if (split > rows) split = rows;
+  nsf_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(g, scratch, rows, map, grad, loss_parts, map0, split);
   NSF_CUDA_OK(cudaGetLastError());
   return NSF_OK;
 }
@@ -164,7 +178,7 @@ int nsf_pack_launch(const NsfNetGeom& g, const float* flat, float* pk, nsf_strea
 }
 
 int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, const int* map, float* grad,
-                        float* loss_parts, nsf_stream_t) {
+                        float* loss_parts, nsf_stream_t, const int*, int) {
   const long long stride = g.gs_row();
   if (grad)
     for (int i = 0; i < g.n_params; ++i) {

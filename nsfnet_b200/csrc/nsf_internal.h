@@ -60,7 +60,6 @@ struct NsfCtx {
   float* e_buf = nullptr;     // [cap] EVM output at the collocation points
   float* ebar_buf = nullptr;  // [cap] d(loss)/d(e)
   long long cap = 0;
-  void* umma = nullptr;  // tcgen05 path state, round-1 kernel: neurons on M, 8-point tiles (nsf_umma_jet.cu)
   void* pm = nullptr;    // tcgen05 path state, points-on-M kernel (nsf_pm_jet.cu)
   void* side = nullptr;     // side stream: the data blocks (boundary / supervised MSE) run beside the EVM forward + jet kernel
   void* ev_fork = nullptr;
@@ -80,7 +79,7 @@ int nsf_ffma_occupancy(int ns, int hp);
 int nsf_ffma_launch(NsfKernelArgs& a, int ns, int grid, nsf_stream_t st);
 int nsf_pack_launch(const NsfNetGeom& g, const float* flat, float* pk, nsf_stream_t st);
 int nsf_finalize_launch(const NsfNetGeom& g, const float* scratch, int rows, const int* map, float* grad,
-                        float* loss_parts, nsf_stream_t st);
+                        float* loss_parts, nsf_stream_t st, const int* map0 = nullptr, int split = 0);
 int nsf_adam_launch(float* params, const float* grad, float* m, float* v, long long n, float lr, float b1, float b2,
                     float eps, float bc1, float bc2, float grad_scale, nsf_stream_t st);
 
@@ -92,20 +91,13 @@ int nsf_value_fwd_supported(const NsfNetGeom& g);
 int nsf_value_fwd_launch(const NsfNetGeom& g, int sms, const float* flat, const float* x, const float* y, long long n, float* out,
                          nsf_stream_t st);
 
-// nsf_umma_jet.cu (CUDA build only) ---------------------------------------------------------------
-int nsf_umma_supported(const NsfNetGeom& g);
-int nsf_umma_group_points();
-int nsf_umma_init(NsfCtx* ctx);
-void nsf_umma_free(NsfCtx* ctx);
-int nsf_umma_stage_cycles(NsfCtx* ctx, double* out);
-int nsf_umma_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
-
 // nsf_pm_jet.cu (CUDA build only): points-on-M tcgen05 kernel, hidden = 80 and hidden = 120 ------------------------
 int nsf_pm_supported(const NsfNetGeom& g);
 int nsf_pm_tile_points(const NsfNetGeom& g);
 int nsf_pm_init(NsfCtx* ctx);
 void nsf_pm_free(NsfCtx* ctx);
 int nsf_pm_grid(NsfCtx* ctx, long long n);
+const int* nsf_pm_map(NsfCtx* ctx);
 int nsf_pm_stage_cycles(NsfCtx* ctx, double* out);
 int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params, int* grid_out, nsf_stream_t st, int* launches);
 

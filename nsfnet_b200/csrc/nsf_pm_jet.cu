@@ -35,12 +35,36 @@
 #include "nsf_tc.cuh"
 #include "nsf_jet_math.cuh"
 #include <cstdlib>
+#include <type_traits>
+#include <vector>
 
 using namespace nsftc;
 
 namespace {
 
-constexpr int FLUSH = 16;   // tiles between flushes of the TMEM weight-gradient accumulators (bounds the truncating accumulations)
+// The tensor core rounds TOWARD ZERO every time it adds into the fp32 accumulator (one truncation per MMA: scripts/emu_tc_numerics.py
+// reproduces the errors measured on the B200).  The bias does not average out in a gradient that is a sum of cancelling terms: at
+// trained weights a single K = 80 / 120 chain put the weight gradient 3 - 6x further from the fp64 truth than the reference's own
+// fp32 path (profiles/r2_parity_trained_before_fix.txt).  Hence
+//   * the full-magnitude hi * hi products of a contraction are spread over NACC accumulators (chains of 3 - 5 MMAs), summed by the
+//     epilogue in fp32 round-to-nearest;
+//   * a weight-gradient accumulator lives for ONE tile and one layer: it is added to the CTA's gradient row (red.global.add, L2)
+//     as soon as its MMAs have completed.
+// Measured with the bit-exact model of the accumulation (scripts/emu_tc_numerics.py): the bias of the FORWARD chains is what
+// moves the gradient; that of the dgrad chains does not (a relative 1e-7 on the adjoints).  Forward stages therefore use NACC_F
+// accumulators (the weight-gradient accumulator is free then: all 512 columns), reverse stages NACC_R.
+#ifndef NSF_PM_NACC_F128
+#define NSF_PM_NACC_F128 4
+#endif
+#ifndef NSF_PM_NACC_R128
+#define NSF_PM_NACC_R128 1
+#endif
+#ifndef NSF_PM_NACC_F64
+#define NSF_PM_NACC_F64 4
+#endif
+#ifndef NSF_PM_NACC_R64
+#define NSF_PM_NACC_R64 1
+#endif
 
 template <int H_, int MT_>
 struct Cfg {
@@ -52,12 +76,18 @@ struct Cfg {
   static constexpr int NG = KS / GK;             // weight blocks per part (hi / lo) and stage
   static constexpr int NB = H;                   // N of the forward / dgrad MMAs
   static constexpr int DWN = ((H + 15) / 16) * 16;  // N of the weight-gradient MMAs (M = 128 needs N % 16 == 0)
+  static constexpr int NACC_F = MT == 128 ? NSF_PM_NACC_F128 : NSF_PM_NACC_F64;   // accumulators of a forward contraction (columns [0, NACC_F * NB))
+  static constexpr int NACC_R = MT == 128 ? NSF_PM_NACC_R128 : NSF_PM_NACC_R64;   // accumulators of a dgrad contraction (behind the weight gradient's)
   static constexpr int NSUB = MT == 128 ? 4 : 3; // epilogue warps per TMEM quadrant
   static constexpr int NEW = 4 * NSUB;           // epilogue warps
   static constexpr int NWORK = MT == 128 ? NSUB : 2 * NSUB;  // workers (warps resp. half-warps) per quadrant
   static constexpr int CW = 4 * NWORK;           // neurons per chunk: chunk c = neurons [CW c, CW (c+1)), 4 per worker
   static constexpr int NCH = H / CW;             // chunks per stage (= 4-neuron pieces per worker)
   static constexpr int KPC = CW / 8;             // k-steps of the next contraction that one chunk completes
+  static constexpr int WCOLS = 4 * NCH;          // D columns of one worker: its neurons of every chunk side by side, so that one wide
+                                                 // tcgen05.ld fetches them all.  Neuron n = CW c + 4 w + i  <->  column WCOLS w + 4 c + i
+                                                 // (the row order of the weight images: nsf_pm_pack_kernel)
+  __host__ __device__ static constexpr int dcol(int n) { return WCOLS * ((n % CW) / 4) + 4 * (n / CW) + (n % 4); }
   static constexpr int NEPI = NEW * 32;
   static constexpr int NTHREADS = (NEW + 2) * 32;
   static constexpr uint32_t GRP = (H / 4) * 512; // one 32-row group of one image part
@@ -76,6 +106,13 @@ struct Cfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory");
   static_assert(OFF_Q % 1024 == 0 && OFF_WHI % 1024 == 0 && PART % 1024 == 0, "swizzle phase");
 };
+
+// Position of dW_l[j][k] inside the H * H block of a gradient row written by this kernel: the order in which the epilogue
+// drains the accumulator (TMEM lane = j, 4 columns per instruction), so that the additions are coalesced.
+__host__ __device__ inline int pm_dw_index(int H, int nsub, int j, int k) {
+  const int cpw = H / nsub, q = j >> 5, lane = j & 31, nl = H - 32 * q < 32 ? H - 32 * q : 32;
+  return q * 32 * H + ((k / cpw) * (cpw / 4) + ((k % cpw) >> 2)) * (nl * 4) + lane * 4 + (k & 3);
+}
 
 struct PArgs {
   NsfNetGeom g;
@@ -98,6 +135,7 @@ struct Misc {
   uint64_t ready[5];     // chunk c of the next MMA stage's operands written, previous results consumed (one arrival per epilogue warp)
   uint64_t dfull;        // forward / dgrad MMAs of the stage complete
   uint64_t wdone[4];     // weight-gradient MMAs over row group q complete (P / Q rows of the group may be rewritten)
+  uint64_t dwfree;       // the weight-gradient accumulator has been drained to the gradient row (one arrival per epilogue warp)
   uint64_t hi_full[3], hi_free[3], lo_full[2], lo_free[2];
   uint32_t tmem_base, pad;
   float loss[4][12];     // per TMEM quadrant: w eq1^2, w eq2^2, w eq3^2, w eq4^2, vis_t, count, gbL[0..2]
@@ -119,6 +157,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t layout_type) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29); }
 __host__ __device__ constexpr uint32_t lbo_field(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
 
@@ -135,6 +176,28 @@ template <int MT, int HALF>
 __device__ __forceinline__ void st_d4(uint32_t taddr, const float* v) {
   if (MT == 128) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
   else asm volatile("tcgen05.st.sync.aligned.16x32bx2.x4.b32 [%0], %5, {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "n"(HALF) : "memory");
+}
+
+// this thread's 4 * NCH consecutive D columns (a worker's neurons are adjacent columns: Cfg::dcol): one x16 and one x4 load
+template <int MT, int HALF, int NCH>
+__device__ __forceinline__ void ld_dall(uint32_t taddr, float (&d)[NCH][4]) {
+  static_assert(NCH == 5, "20 columns per worker");
+  uint32_t r[20];
+  if (MT == 128) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16));
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16], %17;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr), "n"(HALF));
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(taddr + 16), "n"(HALF));
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[c][i] = __uint_as_float(r[4 * c + i]);
 }
 
 // lane s of a quad holds v[i] = (stream s, neuron i); afterwards lane i holds w[s] = (stream s, neuron i)   (scripts/probe_pm.cu)
@@ -165,13 +228,22 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   using C = Cfg<H, MT>;
   using MiscT = Misc<H, L, C::GWL_SMEM ? 4 : 0>;
   static_assert(sizeof(MiscT) <= C::MISC, "misc region too small");
-  static_assert((L - 1) * C::DWN + C::NB <= 512, "tensor memory columns");
+  static_assert(C::DWN + C::NACC_R * C::NB <= 512 && C::NACC_F * C::NB <= 512, "tensor memory columns");
   extern __shared__ __align__(1024) uint8_t smem[];
   MiscT* misc = reinterpret_cast<MiscT*>(smem + C::OFF_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const NsfNetGeom& g = a.g;
   constexpr int NMS = TRAIN ? 2 * L - 1 : L;          // MMA stages per tile
-  constexpr uint32_t DCOL = (L - 1) * C::DWN;         // D (forward / dgrad results) behind the weight-gradient accumulators
+#ifdef NSF_PM_DCOL_F
+  constexpr uint32_t DCOL_F = NSF_PM_DCOL_F;
+#else
+  constexpr uint32_t DCOL_F = 0;
+#endif
+#ifdef NSF_PM_DCOL_R
+  constexpr uint32_t DCOL = NSF_PM_DCOL_R;
+#else
+  constexpr uint32_t DCOL = C::DWN;                   // reverse stages: accumulators of NB columns behind the weight-gradient accumulator (columns [0, DWN))
+#endif
   const uint32_t smem_base = smem_u32(smem);
   const bool dbg = a.dbg != nullptr;
 
@@ -181,6 +253,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
     for (int i = 0; i < 5; ++i) mbar_init(&misc->ready[i], C::NEW);
     mbar_init(&misc->dfull, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&misc->wdone[i], 1);
+    mbar_init(&misc->dwfree, C::NEW);
     for (int i = 0; i < 3; ++i) { mbar_init(&misc->hi_full[i], 1); mbar_init(&misc->hi_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&misc->lo_full[i], 1); mbar_init(&misc->lo_free[i], 1); }
     mbar_fence_init();
@@ -192,6 +265,15 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   }
   // the weight-gradient MMAs (M = 128) read image rows past the H real neurons: keep them finite
   for (uint32_t i = tid * 16; i < 2 * C::IMG; i += C::NTHREADS * 16) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef NSF_PM_NOZERO
+  if (TRAIN && a.scratch) {   // the hidden-layer weight gradients are accumulated into the row tile by tile
+    float* grow = a.scratch + (size_t)blockIdx.x * g.gs_row();
+    for (int l = 1; l < L; ++l) {
+      float4* w4 = reinterpret_cast<float4*>(grow + g.gs_w(l));
+      for (int i = tid; i < H * g.HP / 4; i += C::NTHREADS) w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#endif
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -202,19 +284,24 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   if (warp == C::NEW) {
     // =========================== issuer warp ===========================
     const uint32_t leader = elect_one();
-    const uint32_t sb4 = smem_base >> 4;
-    uint32_t ready_ph = 0, stage_ctr = 0, lo_ctr0 = 0, lo_ctr1 = 0;
+    const uint32_t sb4_0 = smem_base >> 4;
+    uint32_t ready_ph = 0, stage_ctr = 0, lo_ctr0 = 0, lo_ctr1 = 0, wg_ctr = 0;
     long long c_wait = 0, c_issue = 0, c_wwait = 0;
     constexpr uint32_t AHI = desc_hi_t(512, 1), BHI = desc_hi(256);
     for (int t = 0; t < my_tiles; ++t) {
-      const bool zero_dw = (t % FLUSH) == 0;
 #pragma unroll 1
       for (int ms = 0; ms < NMS; ++ms) {
         const int s = ms + 1;
         const bool outst = (s == L);
         const uint32_t wsub = outst ? C::WSUB_O : C::WSUB;
         const uint32_t idesc = idesc_tf32(MT, outst ? 16 : C::NB, 1, 0);
-        const uint32_t d_col = tmem + DCOL;
+        // Every descriptor below is a constant offset from the shared-memory base.  Left alone, the compiler hoists all ~150 of them out
+        // of the stage loop and then SPILLS them: local-memory reloads between the MMAs of the one issuing thread cost 1.5 ms per 1e6
+        // points (9.1 against 7.6 ms).  The opaque copy makes them loop-variant: one integer add per operand instead.
+        uint32_t sb4 = sb4_0;
+        asm volatile("" : "+r"(sb4));
+        const bool fwd_stage = s <= L;
+        const uint32_t d_col = tmem + (fwd_stage ? DCOL_F : DCOL);
         long long t0 = 0, t1 = 0;
         const uint32_t a_hi = sb4 + (C::OFF_P >> 4) + lbo_field(C::GRP), a_lo = a_hi + (C::PART >> 4);
         // The epilogue hands the operand image over chunk by chunk (CW neurons = KPC k-steps of this contraction): the two
@@ -260,8 +347,12 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
 #pragma unroll
           for (int kk = 0; kk < C::GK; ++kk) {
-            const uint32_t da = (uint32_t)((gi * C::GK + kk) * 1024) >> 4, dw = (kk * wsub) >> 4;
-            mma_tf32_elect2(d_col, a_hi + da, AHI, w_hi + dw, BHI, idesc, 1, leader);
+            // accumulator 0 holds the corrections; the others start from zero with their first k-step
+            const int ks = gi * C::GK + kk;
+            const int ac = fwd_stage ? ks * C::NACC_F / C::KS : ks * C::NACC_R / C::KS;
+            const bool fresh = ac > 0 && (fwd_stage ? (ks - 1) * C::NACC_F / C::KS : (ks - 1) * C::NACC_R / C::KS) != ac;
+            const uint32_t da = (uint32_t)(ks * 1024) >> 4, dw = (kk * wsub) >> 4;
+            mma_tf32_elect2(d_col + (uint32_t)(ac * C::NB), a_hi + da, AHI, w_hi + dw, BHI, idesc, fresh ? 0 : 1, leader);
           }
           mma_commit_elect(&misc->hi_free[gi], leader);
         }
@@ -270,8 +361,15 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         ++stage_ctr;
         if (TRAIN && s > L) {
           // weight gradient of layer l = 2L - s: dW_l[128, DWN] += P[rows, j]^T Q[rows, k], both images read K-major (type 1)
-          const int l = 2 * L - s;
-          const uint32_t dw_col = tmem + (uint32_t)((l - 1) * C::DWN);
+#ifdef NSF_PM_DWPERLAYER
+          const uint32_t dw_col = tmem + (uint32_t)((2 * L - s - 1) * C::DWN);
+#else
+          const uint32_t dw_col = tmem;
+#endif
+#ifndef NSF_PM_NODWFREE
+          if (wg_ctr >= 1) { mbar_wait_relaxed(&misc->dwfree, (wg_ctr - 1) & 1u, 32); tc_fence_after(); }   // previous contents drained
+#endif
+          ++wg_ctr;
           const uint32_t wdesc = idesc_tf32(128, C::DWN, 0, 0);
           const uint32_t p_hi = sb4 + (C::OFF_P >> 4), p_lo = p_hi + (C::PART >> 4);
           const uint32_t q_hi = sb4 + (C::OFF_Q >> 4), q_lo = q_hi + (C::PART >> 4);
@@ -280,7 +378,11 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
             for (int kr = 0; kr < 4; ++kr) {
               const uint32_t o = (uint32_t)(qq * C::GRP + kr * 32) >> 4;
-              mma_tf32_elect2(dw_col, p_lo + o, AHI, q_hi + o, AHI, wdesc, !(zero_dw && qq == 0 && kr == 0), leader);
+#ifdef NSF_PM_ACC1
+              mma_tf32_elect2(dw_col, p_lo + o, AHI, q_hi + o, AHI, wdesc, 1, leader);
+#else
+              mma_tf32_elect2(dw_col, p_lo + o, AHI, q_hi + o, AHI, wdesc, !(qq == 0 && kr == 0), leader);
+#endif
               mma_tf32_elect2(dw_col, p_hi + o, AHI, q_lo + o, AHI, wdesc, 1, leader);
               mma_tf32_elect2(dw_col, p_hi + o, AHI, q_hi + o, AHI, wdesc, 1, leader);
             }
@@ -337,7 +439,9 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // chunk c = neurons [CW c, CW (c + 1)); this worker's piece of it is neurons CW c + 4 worker + (0..3)
     // TMEM address of this worker's D columns in chunk 0 (MT = 64: the upper half-warp reads 4 columns further); chunk c: + CW c
-    const uint32_t d_thr = tmem + lane_addr + DCOL + (uint32_t)(MT == 128 ? 4 * worker : 8 * sub);
+    const uint32_t d_thr_0 = tmem + lane_addr + (uint32_t)(MT == 128 ? C::WCOLS * worker : 2 * C::WCOLS * sub);   // (MT = 64: the upper half-warp reads WCOLS columns further)
+    const uint32_t d_thr_f = d_thr_0 + DCOL_F;                                                  // forward stages
+    const uint32_t d_thr = d_thr_0 + DCOL;                                                      // reverse stages
     // byte offset of this thread's float4 (neuron 4 worker + kq of chunk 0) inside an image part; chunk c: + CSTR c
     const uint32_t img_thr = (uint32_t)(pt_loc >> 3) * C::GRP + (uint32_t)worker * 512u + (uint32_t)kq * 128u +
                              (uint32_t)((((pt_loc >> 1) & 3) ^ kq) * 32) + (uint32_t)(pt_loc & 1) * 16u;
@@ -367,6 +471,54 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&misc->ready[c]);
+    };
+
+    // this worker's D cells of every chunk, the NA accumulators summed in fp32 (round to nearest), two accumulators per round trip
+    auto load_d = [&](uint32_t base, auto na_tag, float (&d)[C::NCH][4]) {
+      constexpr int NA = decltype(na_tag)::value;
+#pragma unroll
+      ld_dall<MT, C::WCOLS, C::NCH>(base, d);
+      if (NA == 1) tmem_ld_wait();
+#pragma unroll
+      for (int ac = 1; ac < NA; ac += 2) {
+        float e[C::NCH][4], f[C::NCH][4];
+        ld_dall<MT, C::WCOLS, C::NCH>(base + (uint32_t)(ac * C::NB), e);
+        if (ac + 1 < NA) ld_dall<MT, C::WCOLS, C::NCH>(base + (uint32_t)((ac + 1) * C::NB), f);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[c][i] += (ac + 1 < NA) ? e[c][i] + f[c][i] : e[c][i];
+      }
+    };
+    // dW_l (TMEM lane = output neuron j, column = input neuron k) of the tile -> added to this CTA's gradient row.  Every element
+    // of the row is only ever touched by one thread, in program order: the sums are bit-reproducible.  Then the accumulator is free.
+    float* const grow = TRAIN ? a.scratch + (size_t)blockIdx.x * g.gs_row() : nullptr;
+    auto flush_dw = [&](int l) {
+      constexpr int CPW = H / C::NSUB;                  // columns per warp of a quadrant
+      static_assert(H % C::NSUB == 0 && CPW % 20 == 0, "flush split");
+      tc_fence_after();
+#ifndef NSF_PM_NOFLUSH
+      if (q * 32 < H) {                                 // (warp-uniform) this quadrant holds real rows
+        // drain order (pm_dw_index): a warp instruction adds nl x 16 contiguous bytes
+        const int nl = H - 32 * q < 32 ? H - 32 * q : 32;
+        float* dst = grow + g.gs_w(l) + q * 32 * H + (sub * (CPW / 4)) * (nl * 4) + (lane < nl ? lane : 0) * 4;
+#pragma unroll
+        for (int h = 0; h < CPW; h += 20) {
+          float v[20];
+#pragma unroll
+          for (int i = 0; i < 20; i += 4) tmem_ld4(tmem + lane_addr + (uint32_t)(sub * CPW + h + i), v + i);
+          tmem_ld_wait();
+          if (lane < nl) {
+#pragma unroll
+            for (int i = 0; i < 20; i += 4) red_add_v4(dst + ((h + i) / 4) * (nl * 4), v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      }
+#endif
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&misc->dwfree);
     };
 
     for (int t = 0; t < my_tiles; ++t) {
@@ -405,9 +557,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         tc_fence_after();
         if (dbg) { t1 = clock64(); c_dwait += t1 - t0; c_dw_fwd += t1 - t0; }
         float d[C::NCH][4];
-#pragma unroll
-        for (int c = 0; c < C::NCH; ++c) ld_d4<MT, 4>(d_thr + C::CW * c, d[c]);
-        tmem_ld_wait();
+        load_d(d_thr_f, std::integral_constant<int, C::NACC_F>(), d);
 #pragma unroll
         for (int c = 0; c < C::NCH; ++c) {      // all transposes first: the hand-over fences below pin the shuffles in place
           float z[4];
@@ -450,8 +600,18 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         tc_fence_after();
         if (dbg) { t1 = clock64(); c_dwait += t1 - t0; c_dw_fwd += t1 - t0; }
         float o[4];
-        ld_d4<MT, 4>(tmem + lane_addr + DCOL, o);           // this row's (u, v, p, -) of stream kq
-        tmem_ld_wait();
+        {                                                   // this row's (u, v, p, -) of stream kq, every accumulator
+          float e[C::NACC_F][4];
+#pragma unroll
+          for (int ac = 0; ac < C::NACC_F; ++ac) ld_d4<MT, 4>(tmem + lane_addr + DCOL_F + (uint32_t)(ac * C::NB), e[ac]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o[i] = e[0][i];
+#pragma unroll
+            for (int ac = 1; ac < C::NACC_F; ++ac) o[i] += e[ac][i];
+          }
+        }
         if (MT == 64) {                                     // the upper half-warp read the neighbouring columns: take the lower one's
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = __shfl_sync(0xffffffffu, o[i], lane & 15);
@@ -568,9 +728,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           tc_fence_after();
           if (dbg) { t1 = clock64(); c_dwait += t1 - t0; c_dw_rev += t1 - t0; }
           float d[C::NCH][4];
-#pragma unroll
-          for (int c = 0; c < C::NCH; ++c) ld_d4<MT, 4>(d_thr + C::CW * c, d[c]);
-          tmem_ld_wait();
+          load_d(d_thr, std::integral_constant<int, C::NACC_R>(), d);
           if (lm1 >= 1) {
 #pragma unroll
             for (int c = 0; c < C::NCH; ++c) {
@@ -579,7 +737,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
               nsf_zbar_from(stc[c], ab, zb);
               const float sb0 = red_pts(zb[0]);
               if (red_lane) misc->gb[q][lm1][k0 + C::CW * c] += sb0;
-              st_d4<MT, 4>(d_thr + C::CW * c, zb);     // park zbar_{l-1} in this thread's own (now free) D cells
+              st_d4<MT, C::WCOLS>(d_thr + 4 * c, zb);  // park zbar_{l-1} in this thread's own (now free) D cells
             }
             // a_{l-2} comes from the stash alone; the loads fly while this warp waits for the weight-gradient MMAs
 #pragma unroll
@@ -591,8 +749,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
             ++rs_ctr;
             if (dbg) { t1 = clock64(); c_wwait += t1 - t0; }
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < C::NCH; ++c) ld_d4<MT, 4>(d_thr + C::CW * c, d[c]);
+            ld_dall<MT, C::WCOLS, C::NCH>(d_thr, d);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < C::NCH; ++c) {
@@ -607,6 +764,11 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
               }
               chunk_done(c);
             }
+            // every weight-gradient MMA of this stage (layer lm1 + 1), not only those over this thread's rows
+#ifndef NSF_PM_NOFLUSHCALL
+            if (rg != C::NQ - 1) mbar_wait(&misc->wdone[C::NQ - 1], (rs_ctr - 1) & 1u);
+            flush_dw(lm1 + 1);
+#endif
             if (dbg) { t0 = clock64(); c_work += t0 - t1; c_rb += t0 - t1; }
           } else {
             // layer 0: its weight gradient (K = 2) and bias gradient on FFMA; nothing goes back to the tensor core
@@ -625,38 +787,13 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
             for (int i = 0; i < C::NQ; ++i) mbar_wait(&misc->wdone[i], rs_ctr & 1u);
             ++rs_ctr;
-            tc_fence_before();
             if (dbg) c_wwait += clock64() - t0;
+#ifndef NSF_PM_NOFLUSHCALL
+            flush_dw(1);
+#else
+            tc_fence_before();
+#endif
           }
-        }
-        if ((t + 1) % FLUSH == 0 || t == my_tiles - 1) {
-          // dW_l accumulators (TMEM lane = j, columns (l-1)*DWN + k) -> this CTA's gradient row; every weight-gradient MMA has
-          // completed (all wdone barriers were waited on above), the next one is issued L stages from here
-          tc_fence_after();
-          float* grow = a.scratch + (size_t)blockIdx.x * g.gs_row();
-          const bool first = t < FLUSH;
-          const int j = q * 32 + lane;
-          for (int l = 1 + sub; l < L; l += C::NSUB) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < C::DWN; c0 += 16) {
-              float v[16];
-              tmem_ld16(tmem + lane_addr + (uint32_t)((l - 1) * C::DWN + c0), v);
-              tmem_ld_wait();
-              if (j < H) {
-                float* dst = grow + g.gs_w(l) + (size_t)j * g.HP + c0;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  if (c0 + i < H) {
-                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    float4* d4 = reinterpret_cast<float4*>(dst + i);
-                    if (!first) { const float4 p = *d4; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                    *d4 = o;
-                  }
-                }
-              }
-            }
-          }
-          tc_fence_before();
         }
       }
     }
@@ -703,7 +840,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   if (warp == C::NEW) tmem_dealloc(tmem, 512);
 }
 
-// weight stage images: thread per (image, n, k).  Element (n, k) of part p lives at
+// weight stage images: thread per (image, n, k).  Element (r = row of n, k) of part p lives at
 //   p * NG * WBLK + (k / 40) * WBLK + ((k % 40) / 8) * (N_img * 32) + (n / 8) * 256 + ((k / 4) & 1) * 128 + (n % 8) * 16 + (k % 4) * 4
 template <int H, int MT>
 __global__ void nsf_pm_pack_kernel(NsfNetGeom g, const float* __restrict__ flat, uint8_t* __restrict__ wimg) {
@@ -729,8 +866,9 @@ __global__ void nsf_pm_pack_kernel(NsfNetGeom g, const float* __restrict__ flat,
   }
   float hi, lo;
   split_tf32(v, hi, lo);
+  const int r = img == L - 1 ? n : C::dcol(n);     // image row = D column of the result (hidden layers: Cfg::dcol)
   const size_t off = (size_t)img * C::WSTAGE + (size_t)(k / (8 * C::GK)) * C::WBLK + (size_t)((k % (8 * C::GK)) / 8) * (nrows * 32) +
-                     (size_t)(n >> 3) * 256 + (size_t)((k >> 2) & 1) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4;
+                     (size_t)(r >> 3) * 256 + (size_t)((k >> 2) & 1) * 128 + (size_t)(r & 7) * 16 + (size_t)(k & 3) * 4;
   *reinterpret_cast<float*>(wimg + off) = hi;
   *reinterpret_cast<float*>(wimg + off + (size_t)C::NG * C::WBLK) = lo;
 }
@@ -739,6 +877,7 @@ struct PmState {
   uint8_t* wimg = nullptr;
   float* stash = nullptr;
   long long* dbg = nullptr;
+  int* map = nullptr;          // flat parameter index -> offset inside one of THIS kernel's gradient rows
   int dbg_on = 0, last_grid = 0, grid = 0;
   size_t wstage = 0;
 };
@@ -786,6 +925,18 @@ int nsf_pm_init(NsfCtx* ctx) {
   NSF_CUDA_OK(cudaMalloc((void**)&s->wimg, wbytes));
   NSF_CUDA_OK(cudaMemset(s->wimg, 0, wbytes));
   NSF_CUDA_OK(cudaMalloc((void**)&s->stash, sbytes));
+  {
+    std::vector<int> map(g.n_params);
+    const int nsub = g.H == 80 ? Cfg<80, 128>::NSUB : Cfg<120, 64>::NSUB;
+    for (int i = 0; i < g.n_params; ++i) {
+      int o = nsf_flat_to_gs(g, i);
+      for (int l = 1; l < g.L; ++l)
+        if (o >= g.gs_w(l) && o < g.gs_w(l) + g.H * g.HP) { const int r = o - g.gs_w(l); o = g.gs_w(l) + pm_dw_index(g.H, nsub, r / g.HP, r % g.HP); break; }
+      map[i] = o;
+    }
+    NSF_CUDA_OK(cudaMalloc((void**)&s->map, sizeof(int) * g.n_params));
+    NSF_CUDA_OK(cudaMemcpy(s->map, map.data(), sizeof(int) * g.n_params, cudaMemcpyHostToDevice));
+  }
   for (int train = 0; train < 2; ++train)
     NSF_CUDA_OK(cudaFuncSetAttribute(pm_kernel(g.H, g.L, train != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ctx->ws_bytes += (long long)(wbytes + sbytes);
@@ -796,10 +947,13 @@ int nsf_pm_init(NsfCtx* ctx) {
 void nsf_pm_free(NsfCtx* ctx) {
   PmState* s = (PmState*)ctx->pm;
   if (!s) return;
-  cudaFree(s->wimg); cudaFree(s->stash); if (s->dbg) cudaFree(s->dbg);
+  cudaFree(s->wimg); cudaFree(s->stash); cudaFree(s->map); if (s->dbg) cudaFree(s->dbg);
   delete s;
   ctx->pm = nullptr;
 }
+
+// gradient-row layout of the rows this kernel writes (nsf_finalize_launch)
+const int* nsf_pm_map(NsfCtx* ctx) { return ((PmState*)ctx->pm)->map; }
 
 // rows (CTAs) the launch for n points writes
 int nsf_pm_grid(NsfCtx* ctx, long long n) {

@@ -197,11 +197,10 @@ def test_full_size_properties(gu):
 
 # ---- tcgen05 (3xTF32) path: same bar as the FP32 path -------------------------------------------------
 @pytest.mark.parametrize("H,L,n,nb,path", [(80, 6, 1333, 132, 3), (80, 2, 16, 8, 3), (80, 3, 5, 3, 3), (80, 6, 100000, 2052, 3), (80, 4, 777, 40, 3),
-                                           (80, 5, 4736, 17, 3), (120, 4, 1333, 132, 3), (120, 2, 16, 8, 3), (120, 3, 5, 3, 3), (120, 4, 100000, 2052, 3),
-                                           (80, 6, 1333, 132, 2), (80, 2, 16, 8, 2), (80, 6, 100000, 2052, 2)])
+                                           (80, 5, 4736, 17, 3), (120, 4, 1333, 132, 3), (120, 2, 16, 8, 3), (120, 3, 5, 3, 3), (120, 4, 100000, 2052, 3)])
 @pytest.mark.parametrize("has_evm", [False, True])
 def test_umma_step_matches_oracle(gu, H, L, n, nb, has_evm, path):
-    """tcgen05 kernels: path 3 = points on M (hidden 80 and 120), path 2 = the round-1 kernel (hidden 80)."""
+    """tcgen05 kernel (path 3, points on M): hidden 80 and 120, every layer count."""
     rng = np.random.default_rng(L * 100 + n)
     md, ed = J.NetDesc(2, 3, L, H), J.NetDesc(2, 1, 4, 40)
     pm, pe = J.init_params(md, 1) * 1.5, J.init_params(ed, 2)
@@ -235,7 +234,7 @@ def test_umma_step_matches_oracle(gu, H, L, n, nb, has_evm, path):
     assert np.array_equal(o["grad_main"], o2["grad_main"])
 
 
-@pytest.mark.parametrize("path", [2, 3])
+@pytest.mark.parametrize("path", [3])
 def test_umma_golden_ev_lag(gu, golden_dir, path):
     g = np.load(os.path.join(golden_dir, "ev_re2000_lag.npz"))
     xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))

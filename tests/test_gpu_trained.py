@@ -6,7 +6,9 @@ away from the same graph evaluated in fp64, so two fp32 evaluation orders cannot
 tests/golden/trained_*.npz (tests/golden/make_golden_r2.py) hold, for the state the UNMODIFIED reference reached after 3000 / 2000
 Adam steps (N_f = 4000, 516 boundary points), the reference's fp32 outputs and its fp64 outputs on the same fp32-valued inputs.
 The bar for every kernel path:   err(kernel, fp64) <= max(1e-5, 2 * err(reference fp32, fp64))
-for residuals, loss and gradient (norm-wise), plus a floored element-wise check.  The measured triples go to
+for residuals, loss and gradient (norm-wise), plus a floored element-wise check: no gradient entry further than
+max(1e-3, 2 x reference) from the truth, relative to |truth| + 1 % of the gradient's rms (the maximum over 38 000 entries is a
+4-sigma statistic of the error, i.e. ~4 x the rel-L2 figure scaled by rms / floor; 1e-3 is that for the 1e-5 norm-wise bar).  The measured triples go to
 gpurun_out/r2_parity_trained.txt (committed as profiles/r2_parity_trained.txt).
 """
 import os
@@ -19,7 +21,7 @@ from oracle import jet_numpy as J
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PATH_NAME = {1: "ffma", 2: "tcgen05 neurons-on-M", 3: "tcgen05 points-on-M"}
+PATH_NAME = {1: "ffma", 3: "tcgen05 points-on-M"}
 
 
 def _bar(err_kernel, err_ref):
@@ -49,8 +51,8 @@ def _check(name, path, o, g, n_eq, n, nb):
     lines.append(f"  gradient rel-L2      {kg:.3e} | {rg:.3e} | {max(1e-5, 2 * rg):.3e}")
     ok &= _bar(kg, rg)
     ke, re_ = _elem(o["grad_main"], g["grad_f64"]), _elem(g["grad_f32"], g["grad_f64"])
-    lines.append(f"  gradient worst elem  {ke:.3e} | {re_:.3e} | {max(1e-4, 2 * re_):.3e}   (relative to |truth| + 1 % rms)")
-    ok &= ke <= max(1e-4, 2.0 * re_)
+    lines.append(f"  gradient worst elem  {ke:.3e} | {re_:.3e} | {max(1e-3, 2 * re_):.3e}   (relative to |truth| + 1 % rms)")
+    ok &= ke <= max(1e-3, 2.0 * re_)
     for i in range(n_eq):
         kr, rr = gu.rel(o["resid"][i], g[f"eq{i+1}_f64"]), gu.rel(g[f"eq{i+1}_f32"], g[f"eq{i+1}_f64"])
         lines.append(f"  eq{i+1} residual rel-L2 {kr:.3e} | {rr:.3e} | {max(1e-5, 2 * rr):.3e}")
@@ -77,7 +79,7 @@ def test_trained_ns(golden_dir, name, path):
     assert _check(name, path, o, g, 3, n, nb)
 
 
-@pytest.mark.parametrize("path", [3, 2, 1])
+@pytest.mark.parametrize("path", [3, 1])
 def test_trained_ev(golden_dir, path):
     from tests import gpu_util as gu
     g = np.load(os.path.join(golden_dir, "trained_ev_re2000.npz"))
@@ -92,7 +94,42 @@ def test_trained_ev(golden_dir, path):
     assert gu.rel(o["e"], g["e_f64"]) <= max(1e-5, 2 * gu.rel(g["e_f32"], g["e_f64"]))
 
 
-@pytest.mark.parametrize("path", [3, 2])
+@pytest.mark.parametrize("name,path", [("trained_ns_re1000", 3), ("trained_ev_re2000", 3), ("trained_ns_re1000", 1)])
+def test_trained_weights_at_scale(golden_dir, name, path):
+    """The goldens above hold 4000 points: one tile per CTA.  Here the trained weights meet 120 000 fresh points (25 / 50 tiles per CTA,
+    so the per-CTA gradient rows are accumulated over many tiles); truth = the fp64 oracle, yardstick = the same oracle in fp32."""
+    from tests import gpu_util as gu
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ev = "params_main" in g.files
+    rng = np.random.default_rng(5)
+    n = 120000
+    x, y = rng.random(n).astype(np.float32), rng.random(n).astype(np.float32)
+    xb, yb, ub, vb = J.cavity_boundary(int(g["n_side"]))
+    nb = xb.size
+    md, ed = (J.NetDesc(2, 3, 6, 80), J.NetDesc(2, 1, 4, 40)) if ev else (J.NetDesc(2, 3, 4, 120), None)
+    pm = g["params_main"] if ev else g["params"]
+    pe = g["params_evm"] if ev else None
+    vtm = (rng.random(n) * 0.02).astype(np.float32) if ev else None
+    phys = J.Physics(Re=float(g["Re"]), alpha_b=10., alpha_evm=float(g["alpha_evm"]) if ev else 0.03, has_evm=ev)
+    kw = dict(evm_flat=pe, evm_desc=ed, vis_t_minus=vtm)
+    r64 = J.step(pm, md, phys, x, y, xb, yb, ub, vb, **kw)
+    r32 = J.step(pm, md, phys, x, y, xb, yb, ub, vb, dtype=np.float32, **kw)
+    abi = gu.Abi(tuple([2, 3, md.n_hidden_layers, md.hidden]), (2, 1, 4, 40) if ev else None, path=path)
+    cp = _capi.physics(float(g["Re"]), alpha_evm=float(g["alpha_evm"]) if ev else 0.03, has_evm=ev)
+    o = abi.step(pm, cp, x, y, blocks=[(xb, yb, ub, vb, None, 10. / nb, 10. / nb, 0.)], params_evm=pe, vtm_in=vtm)
+    assert o["info"]["path"] == path
+    kg, rg = gu.rel(o["grad_main"], r64.grad_main), gu.rel(r32.grad_main, r64.grad_main)
+    lines = [f"{name} at scale ({n} points)  path {path} ({PATH_NAME[path]}): gradient rel-L2 kernel-vs-fp64 {kg:.3e} | fp32 oracle-vs-fp64 {rg:.3e}"]
+    ok = _bar(kg, rg)
+    for i in range(4 if ev else 3):
+        kr, rr = gu.rel(o["resid"][i], r64.eq[i]), gu.rel(r32.eq[i], r64.eq[i])
+        lines.append(f"  eq{i+1} residual rel-L2 {kr:.3e} | {rr:.3e}")
+        ok &= _bar(kr, rr)
+    _report(lines)
+    assert ok
+
+
+@pytest.mark.parametrize("path", [3, 1])
 def test_golden_shipped_boundary_set_and_sdf_weights(golden_dir, path):
     """N_b = 2052: the boundary points come from the reference's own DataLoader.loading_boundary_data(), the SDF weights from
     its cKDTree over them (ev-NSFnet/cavity_data.py:47-94,118-130); production.yaml's nets, 20 000 collocation points."""
