@@ -33,9 +33,6 @@ FLOPS_PER_PT = {"ev": 976_400.0, "ns": 1_305_840.0}      # algor
 EXEC_FLOPS_PER_PT = {"ev": 30 * 80 * 80 * 5 * 0.8 + 9840.0, "ns": 30 * 120 * 120 * 3 * 0.8}  # 4 streams carried (laplacian merged)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture of
-# this command line (profiles/r1_umma_v10_1M_ncu_summary.txt); keyed by (workload, kernel path, points per GPU)
-NCU_TRAFFIC_BYTES = {("ev", 2, 1_000_000): 17.10e6 + 32.02e6}   # stash kept L2-resident (ld/st .cg): profiles/r1_umma_v10_1M_ncu_summary.txt
 
 
 def read_peaks():
@@ -93,11 +90,79 @@ class ClockSampler:
 
 
 def cpu_reference(workload, n_f, steps, warmup):
-    """The reference's algorithm (oracle/autograd_port.py: torch modules + 7 autograd.grad sweeps + backward +
-    Adam, pinned to the reference by tests/golden) on the host cores."""
+    """The reference on the host cores: the UNMODIFIED solvers under baseline/_ref (baseline/ref_arm.py, kind "reference") when that
+    copy is present, else the pinned restatement oracle/autograd_port.py (kind "port": torch modules + 7 autograd.grad sweeps +
+    backward + Adam, bit-identical loss curves to the reference, tests/test_oracle_golden.py).  Returns (pts/s, s/step, threads, kind)."""
+    try:
+        from baseline import ref_arm
+        if ref_arm.available():
+            sec, threads, _ = ref_arm.time_steps(workload, "cpu", n_f, steps, warmup)
+            return n_f / sec, sec, threads, "reference"
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"bench: unmodified reference arm unavailable ({e!r}); timing the pinned port\n")
     from oracle.autograd_port import time_reference_step
     sec, threads = time_reference_step(workload, n_f, steps=steps, warmup=warmup)
-    return n_f / sec, sec, threads
+    return n_f / sec, sec, threads, "port"
+
+
+def reference_cuda_eager(workload):
+    """The unmodified reference's own CUDA path (eager autograd) on this GPU: the same-box competitor."""
+    out = {}
+    try:
+        import torch
+        from baseline import ref_arm
+        if not ref_arm.available():
+            return {"unavailable": "baseline/_ref not present"}
+        for n_f, steps in ((100_000, 5), (500_000, 3)):
+            torch.cuda.reset_peak_memory_stats()
+            sec, _, _ = ref_arm.time_steps(workload, "cuda:0", n_f, steps, 2)
+            out[f"n_f_{n_f}"] = {"ms_per_step": sec * 1e3, "pts_per_s": n_f / sec, "max_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+        out["what"] = "baseline/_ref (verbatim copy of the reference) through its own API: fwd_computing_loss_2d + backward + Adam, full step"
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)[:200]
+    return out
+
+
+def measure_tf32_peak():
+    """Dense TF32 tensor throughput of THIS GPU (torch.matmul 8192^3, allow_tf32): best of 10 (burst) and back to back for 1.5 s."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.time(); k = 0
+        e0.record()
+        while time.time() - t0 < 1.5:
+            for _ in range(20):
+                a @ b
+            k += 20
+            torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        return 2 * n ** 3 / (best * 1e-3) / 1e12, 2 * n ** 3 * k / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def ncu_traffic(workload, path, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed `ncu --set full` capture
+    of this command line (profiles/r2_ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(f"{workload}/path{path}/{n}")
+        return (float(e["bytes"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 def run_reference(args):
@@ -106,13 +171,14 @@ def run_reference(args):
         return
     n_f = args.cpu_n_f
     t0 = time.time()
-    pts_s, sec, threads = cpu_reference(args.workload, n_f, max(1, args.steps), max(1, args.warmup))
+    pts_s, sec, threads, kind = cpu_reference(args.workload, n_f, max(1, args.steps), max(1, args.warmup))
+    what = "the unmodified reference (baseline/_ref) on the host cores" if kind == "reference" else "reference algorithm on the host cores (torch autograd, oracle/autograd_port.py)"
     line = {"impl": "reference", "metric": "collocation_pts_per_s (residual + weight gradient)", "value": pts_s, "unit": "pts/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, n_f_override=n_f), kernel_path="reference algorithm on the host cores (torch autograd, oracle/autograd_port.py)",
+            "config": dict(workload_config(args, n_f_override=n_f), kernel_path=what,
                            l2="n/a (CPU run)", sample_of=f"the {args.n_f}-point workload: {n_f} collocation points per step"),
-            "cpu_baseline": {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": kind,
                              "sample": f"{n_f} collocation pts + 2052 boundary pts per step, full Adam step (N_f=1e6 does not fit host memory for the reference's retained graph)"},
             "e2e": {"value": pts_s, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
@@ -189,6 +255,42 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---- data-parallel identity (W > 1): the all-reduced gradient of W shards == one GPU on the union ----------------------
+    dp_identity = None
+    if world > 1:
+        from nsfnet_b200.solver_core import shard_bounds
+        n_g = 262_144
+        gg = torch.Generator(device=dev).manual_seed(4321)           # the same global set on every rank
+        gx = torch.rand(n_g, device=dev, generator=gg); gy = torch.rand(n_g, device=dev, generator=gg)
+        lo, hi = shard_bounds(n_g, rank, world)
+        P.set_eq_training_shard((gx[lo:hi].clone(), gy[lo:hi].clone()), n_global=n_g)
+        if args.workload == "ev":
+            P.freeze_evm_net(0)
+        loss_dp = float(P._launch_step())
+        g_dp = P._buf[:P._n_main].clone()
+        sync_all()
+        if rank == 0:                                                # one process, whole set, whole boundary, no collective
+            ws, rk, isd = P.world_size, P.rank, P.is_distributed
+            P.world_size, P.rank, P.is_distributed = 1, 0, False
+            try:
+                P.set_boundary_data(cavity_boundary(513))
+                P.set_eq_training_shard((gx, gy), n_global=n_g)
+                if args.workload == "ev":
+                    P.freeze_evm_net(0)
+                loss_1 = float(P._launch_step())
+                g_1 = P._buf[:P._n_main].clone()
+            finally:
+                P.world_size, P.rank, P.is_distributed = ws, rk, isd
+            dp_identity = {"n_f_global": n_g, "grad_rel": float((g_dp - g_1).norm() / g_1.norm()), "loss_rel": abs(loss_dp - loss_1) / abs(loss_1),
+                           "what": f"all-reduced gradient of {world} shards vs the same {n_g} points + 2052 boundary points on one GPU"}
+        sync_all()
+        P.set_boundary_data(cavity_boundary(513))
+        P.set_eq_training_shard((x, y), n_global=n * world)
+        if args.workload == "ev":
+            P.freeze_evm_net(0)
+        if rank == 0 and not (dp_identity["grad_rel"] < 1e-6 and dp_identity["loss_rel"] < 1e-6):
+            raise RuntimeError(f"data-parallel identity violated: {dp_identity}")
 
     # ---- metric (i): residual + weight gradient, inputs resident in HBM -------------------------
     P._ctx.set_timing(True)
@@ -280,6 +382,24 @@ def main():
         if args.workload == "ev":
             P.freeze_evm_net(0)
 
+    # ---- strong scaling: 1e6 collocation points IN TOTAL (BASELINE config 2), fused Adam iterations / s at this N ----------
+    strong = None
+    if not args.no_small:
+        n_t = 1_000_000
+        lo, hi = (rank * (n_t // world), (rank + 1) * (n_t // world) if rank < world - 1 else n_t)
+        x_t = torch.rand(hi - lo, device=dev, generator=g); y_t = torch.rand(hi - lo, device=dev, generator=g)
+        P.set_eq_training_shard((x_t, y_t), n_global=n_t)
+        if args.workload == "ev":
+            P.freeze_evm_net(0)
+        fused_on(P)
+        sps = time_iters(P._fused_step_replayable, 100)
+        P.enable_fused_step(False)
+        strong = {"n_f_total": n_t, "adam_steps_per_s": sps, "pts_per_s": sps * n_t,
+                  "limiter": "fixed per-iteration part (EVM forward, boundary blocks, finalize, Adam, all-reduce), not NCCL bandwidth (152 KB per step)"}
+        P.set_eq_training_shard((x, y), n_global=n * world)
+        if args.workload == "ev":
+            P.freeze_evm_net(0)
+
     # ---- e2e: public API with HOST buffers (pinned), H2D of the points + D2H of the loss every step
     e2e = None
     if not args.no_e2e:
@@ -315,10 +435,18 @@ def main():
     k_ms = float(np.mean(kern_ms))
     flops = FLOPS_PER_PT[args.workload] * n
     achieved = flops / (k_ms * 1e-3) / 1e12
-    peak = 0.5 * bf16_sust          # dense TF32 = 1/2 of the measured sustained bf16 (kernel timed inside a long step)
+    # dense TF32 peak MEASURED on this GPU in this run.  The jet kernel runs at the full SM clock without a power cap (see
+    # `clocks`), so the burst figure is its denominator; the sustained one (power-capped GEMM) is reported beside it.
+    try:
+        tf32_burst, tf32_sust = measure_tf32_peak()
+        peak, peak_note = tf32_burst, "dense TF32 measured in this run: torch.matmul 8192^3, allow_tf32, best of 10 (burst)"
+    except Exception as e:  # noqa: BLE001
+        tf32_burst = tf32_sust = None
+        peak, peak_note = 0.5 * bf16_burst, f"0.5 x bf16_tflops ({how}); the live TF32 measurement failed: {e!r}"
     info = P._ctx.info()
+    traffic, traffic_src = ncu_traffic(args.workload, info["path"], n)
     cfg = workload_config(args)
-    cfg["kernel_path"] = {1: "ffma", 2: "tcgen05-3xtf32, neurons on M (8-point tiles)", 3: "tcgen05-3xtf32, points on M (32 / 16-point tiles)"}[info["path"]]
+    cfg["kernel_path"] = {1: "ffma", 3: "tcgen05-3xtf32, points on M (32 / 16-point tiles)"}[info["path"]]
     line = {"metric": "collocation_pts_per_s (residual + weight gradient)", "value": value, "unit": "pts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -326,21 +454,28 @@ def main():
             "adam_iteration": "nsf_step + device-resident Adam (nsf_adam_dev), one CUDA graph replay per iteration" if world == 1
                               else ("nsf_step + NCCL all-reduce + device-resident Adam (nsf_adam_dev), " +
                                     ("one CUDA graph replay per iteration" if os.environ.get("NSF_FUSED_GRAPH_DDP", "1") == "1" else "launched eagerly")),
-            "adam_small_batch": small,
+            "adam_small_batch": small, "strong": strong,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, info["path"], n)),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "tf32_tflops_burst": tf32_burst, "tf32_tflops_sustained": tf32_sust,
                          "kernel": "collocation jet step (fwd jet + residuals + reverse)", "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / ms_per_step, "flops_per_pt_algorithmic": FLOPS_PER_PT[args.workload],
                          "flops_per_pt_executed": EXEC_FLOPS_PER_PT[args.workload],
-                         "peak_note": f"0.5 x bf16_tflops_sustained ({how}); fp32 FFMA peak 148*128*2*1.965GHz = 74.5 TFLOP/s",
+                         "peak_note": peak_note + "; fp32 FFMA peak 148*128*2*1.965GHz = 74.5 TFLOP/s",
                          "frac_of_ffma_peak": (EXEC_FLOPS_PER_PT[args.workload] * n / (k_ms * 1e-3) / 1e12) / 74.5,
                          "hbm_algorithmic_GBps": 20.0 * n / (k_ms * 1e-3) / 1e9, "hbm_peak_GBps": hbm},
             "gpu_launches": launches, "clocks": clocks}
     if e2e is not None:
         line["e2e"] = e2e
+    if dp_identity is not None:
+        line["dp_identity"] = dp_identity
     if not args.no_cpu_baseline:
-        pts_s, sec, threads = cpu_reference(args.workload, args.cpu_n_f, 3, 1)
-        line["cpu_baseline"] = {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": "port",
+        if world == 1:
+            del P
+            torch.cuda.empty_cache()
+            line["reference_cuda_eager"] = reference_cuda_eager(args.workload)
+        pts_s, sec, threads, kind = cpu_reference(args.workload, args.cpu_n_f, 3, 1)
+        line["cpu_baseline"] = {"value": pts_s, "unit": "pts/s", "cores": threads, "kind": kind,
                                 "sample": f"{args.cpu_n_f} collocation pts + 2052 boundary pts, 3 full Adam steps after 1 warm-up ({sec * 1e3:.0f} ms/step)"}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -157,8 +157,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// The activation stash (36 MB) and the gradient rows (20 MB) are rewritten / re-read all the time and fit the 126 MB L2; under the
+// default replacement policy their dirty lines are still written back as they age: 2.6 - 2.8 GB of DRAM writes per 1e6-point launch of
+// the hidden = 80 kernel (ncu, profiles/r2_pm_ev_1M_ncu_summary.txt; 5 % of the HBM bandwidth, DRAM READS stay at 20 MB: nothing is
+// fetched twice).  An L2 evict_last policy on these accesses removes the write-backs (33 MB per launch) but costs 5 % of the kernel time
+// (8.13 against 7.75 ms; policy on the reductions alone: the same) -- measured, profiles/r2_pm_l2_policy.txt -- so it is off by default.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#ifndef NSF_PM_KEEP
+#define NSF_PM_KEEP 0     // 1: stash stores, 2: stash loads, 4: gradient-row reductions carry the policy
+#endif
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d, uint64_t pol) {
+  if (NSF_PM_KEEP & 4) asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+  else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_keep(float4* addr, const float4 v, uint64_t pol) {
+  if (NSF_PM_KEEP & 1) asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+  else __stcg(addr, v);
+}
+__device__ __forceinline__ float4 ld_keep(const float4* addr, uint64_t pol) {
+  if (!(NSF_PM_KEEP & 2)) return __ldcg(addr);
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr), "l"(pol) : "memory");
+  return v;
 }
 __host__ __device__ constexpr uint32_t desc_hi_t(uint32_t sbo_bytes, uint32_t layout_type) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29); }
 __host__ __device__ constexpr uint32_t lbo_field(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
@@ -457,6 +481,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
       for (int c = 0; c < C::NCH; ++c) gwl[o][c] = 0.f;
     uint32_t dfull_ph = 0, rs_ctr = 0;
+    const uint64_t keep = l2_keep_policy();
     long long c_dwait = 0, c_wwait = 0, c_work = 0, c_s0 = 0, c_fwd = 0, c_out = 0, c_ra = 0, c_rb = 0, c_last = 0, c_dw_fwd = 0, c_dw_rev = 0;
 
     auto red_pts = [&](float v) {      // sum over the points of this worker's rows (fixed tree: deterministic)
@@ -511,7 +536,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           tmem_ld_wait();
           if (lane < nl) {
 #pragma unroll
-            for (int i = 0; i < 20; i += 4) red_add_v4(dst + ((h + i) / 4) * (nl * 4), v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 20; i += 4) red_add_v4(dst + ((h + i) / 4) * (nl * 4), v[i], v[i + 1], v[i + 2], v[i + 3], keep);
           }
         }
       }
@@ -543,7 +568,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
       }
       if (TRAIN) {      // the stash goes to L2 after the hand-overs: fence.proxy.async would wait for these stores
 #pragma unroll
-        for (int c = 0; c < C::NCH; ++c) __stcg(stash_thr + C::CW * c, st0[c]);
+        for (int c = 0; c < C::NCH; ++c) st_keep(stash_thr + C::CW * c, st0[c], keep);
       }
       if (dbg) { t1 = clock64(); c_work += t1 - t0; c_s0 += t1 - t0; }
       // ---------------- stages 1 .. L-1: hidden layers forward ----------------
@@ -574,7 +599,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         }
         if (TRAIN) {    // (t, zx, zy, z_lap) to L2 after the hand-overs: fence.proxy.async would wait for these stores
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) __stcg(stash_thr + s * STL + C::CW * c, make_float4(d[c][0], d[c][1], d[c][2], d[c][3]));
+          for (int c = 0; c < C::NCH; ++c) st_keep(stash_thr + s * STL + C::CW * c, make_float4(d[c][0], d[c][1], d[c][2], d[c][3]), keep);
         }
         if (dbg) { t0 = clock64(); c_work += t0 - t1; c_fwd += t0 - t1; }
       }
@@ -593,7 +618,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         const float bo0 = __ldg(pk + g.pk_bl() + 0), bo1 = __ldg(pk + g.pk_bl() + 1), bo2 = __ldg(pk + g.pk_bl() + 2);
         if (TRAIN) {
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) stl[c] = __ldcg(stash_thr + (L - 1) * STL + C::CW * c);
+          for (int c = 0; c < C::NCH; ++c) stl[c] = ld_keep(stash_thr + (L - 1) * STL + C::CW * c, keep);
         }
         if (dbg) t0 = clock64();
         mbar_wait(&misc->dfull, dfull_ph); dfull_ph ^= 1u;
@@ -677,7 +702,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           // output layer backward on FFMA (3 outputs): adjoint of a_{L-1}, weight gradient of the output layer.
           // a_{L-2} (second operand of the next weight gradient) comes from the stash alone: its loads fly meanwhile.
 #pragma unroll
-          for (int c = 0; c < C::NCH; ++c) stc[c] = __ldcg(stash_thr + (L - 2) * STL + C::CW * c);
+          for (int c = 0; c < C::NCH; ++c) stc[c] = ld_keep(stash_thr + (L - 2) * STL + C::CW * c, keep);
 #pragma unroll
           for (int c = 0; c < C::NCH; ++c) {
             const int k = k0 + C::CW * c;
@@ -741,7 +766,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
             }
             // a_{l-2} comes from the stash alone; the loads fly while this warp waits for the weight-gradient MMAs
 #pragma unroll
-            for (int c = 0; c < C::NCH; ++c) stc[c] = __ldcg(stash_thr + (lm1 - 1) * STL + C::CW * c);
+            for (int c = 0; c < C::NCH; ++c) stc[c] = ld_keep(stash_thr + (lm1 - 1) * STL + C::CW * c, keep);
             tmem_st_wait();
             if (dbg) { t0 = clock64(); c_work += t0 - t1; c_ra += t0 - t1; }
             // the weight-gradient MMAs of this stage still read P and Q: wait for those over this thread's rows

@@ -1,0 +1,34 @@
+"""The one thread that issues tcgen05.mma must not touch local memory between MMAs: a register spill there (the compiler hoists ~150
+loop-invariant descriptors out of the stage loop unless told otherwise) cost 1.5 ms per 1e6 points.  Disassembles the built library and
+reports, per points-on-M kernel, the local loads / stores inside the span of its UTCHMMA instructions.
+Usage: python scripts/check_issuer_spills.py [lib.so]   (exit code 1 if any)"""
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def check(lib):
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    bad, seen = {}, 0
+    for block in out.split("Function : ")[1:]:
+        name = block.split("\n", 1)[0].strip()
+        if "nsf_pm_jet_kernel" not in name:
+            continue
+        lines = block.split("\n")
+        mma = [i for i, l in enumerate(lines) if "UTCHMMA" in l]
+        if not mma:
+            continue
+        seen += 1
+        spills = [i for i in range(mma[0], mma[-1] + 1) if re.search(r"\b(LDL|STL)\b", lines[i])]
+        if spills:
+            bad[name] = len(spills)
+    return seen, bad
+
+
+if __name__ == "__main__":
+    seen, bad = check(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "nsfnet_b200", "libnsf_b200.so"))
+    print(f"{seen} tcgen05 kernels checked;", "no local-memory traffic inside the MMA issue spans" if not bad else f"SPILLS inside the issue span: {bad}")
+    sys.exit(1 if bad else 0)

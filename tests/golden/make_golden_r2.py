@@ -204,6 +204,47 @@ def curve_full(ns, name, Re, seed=0, n_f=10000, steps=5000, every=100, threads=4
     print(name, "fp64-vs-fp32 max deviation", (np.abs(g["curve_fp64"] - g["curve"]) / g["curve"]).max(), flush=True)
 
 
+def curve_early(ns, name, Re, seed=0, n_f=10000, steps=800):
+    """The first 800 Adam steps of the same run, EVERY step: the reference's loop body in fp32 with 4 host threads, again with 1 thread
+    (another summation order of the same fp32 program: the yardstick for 'two fp32 evaluations of this trajectory'), and in fp64."""
+    dl = ref_dataloader("NSFnet", N_f=n_f, N_b=1000)
+    xb, yb, ub, vb = dl.loading_boundary_data()
+    rng = np.random.default_rng(8000 + seed)
+    xf, yf = rng.random((n_f, 1)), rng.random((n_f, 1))
+    curves, params = {}, None
+    for tag, threads in (("fp32_t4", 4), ("fp32_t1", 1)):
+        torch.set_num_threads(threads)
+        torch.manual_seed(seed)
+        P = ns.PysicsInformedNeuralNetwork(Re=Re, layers=4, hidden_size=120, N_f=n_f, bc_weight=10, eq_weight=1)
+        P.set_boundary_data(X=(xb, yb, ub, vb)); P.set_eq_training_data(X=(xf, yf))
+        if params is None:
+            params = flat_params(P.net)
+        P.opt.param_groups[0]["lr"] = 1e-3
+        c, t0 = [], time.time()
+        for k in range(steps):
+            loss, _ = P.fwd_computing_loss_2d()
+            loss.backward(); P.opt.step(); P.opt.zero_grad()
+            c.append(float(loss))
+        curves[tag] = np.array(c, np.float64)
+        print(name, tag, f"{time.time() - t0:.0f}s", c[-1], flush=True)
+    torch.set_num_threads(4)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle.autograd_port import RefSolver
+    s = RefSolver(float(Re), 4, 120, dtype=torch.float64, lr=1e-3)
+    s.net.load_flat(params)
+    s.set_boundary_data((xb, yb, ub, vb))
+    s.set_eq_training_data((xf.astype(np.float32).astype(np.float64), yf.astype(np.float32).astype(np.float64)))
+    c = []
+    for k in range(steps):
+        loss = s.loss_fn(); loss.backward(); s.opt.step(); s.opt.zero_grad()
+        c.append(float(loss.detach()))
+    curves["fp64"] = np.array(c, np.float64)
+    np.savez_compressed(f"{OUT}/{name}.npz", kind="ns_curve_early", Re=Re, params=params, xf=xf.astype(np.float32), yf=yf.astype(np.float32),
+                        steps=steps, lr=1e-3, **{"curve_" + k: v for k, v in curves.items()})
+    d1 = np.abs(curves["fp32_t1"] - curves["fp32_t4"]) / curves["fp32_t4"]; d2 = np.abs(curves["fp64"] - curves["fp32_t4"]) / curves["fp32_t4"]
+    print(name, "1-thread vs 4-thread fp32: max", d1.max(), "at 100/200/400:", d1[100], d1[200], d1[400], "| fp64 vs fp32:", d2[100], d2[200], d2[400], flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "trained"
     ns, ev = load_reference()
@@ -215,6 +256,9 @@ if __name__ == "__main__":
     elif what == "nb2052":
         torch.set_num_threads(4)
         nb2052(ev)
+    elif what == "early":
+        Re = int(sys.argv[2])
+        curve_early(ns, f"curve_early_ns_re{Re}", Re)
     elif what == "curves":
         Re = int(sys.argv[2])
         curve_full(ns, f"curve_full_ns_re{Re}", Re)

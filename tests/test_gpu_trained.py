@@ -155,17 +155,10 @@ def test_golden_shipped_boundary_set_and_sdf_weights(golden_dir, path):
         assert abs(lp[i] / n - g["loss_eq_f32"][i]) < 1e-5 * g["loss_eq_f32"][i]
 
 
-@pytest.mark.parametrize("name", ["curve_full_ns_re100", "curve_full_ns_re1000"])
-def test_full_size_curves_track_reference(golden_dir, name):
-    """BASELINE config 1 at full size: NSFnet 4x120, N_f = 10 000, the reference's 2052 boundary points, Adam
-    lr 1e-3, 5000 steps, loss every 100 steps -- recorded from the reference's own loop body (NSFnet/pinn_solver.py:250-254)
-    on CPU, with the same loop in fp64 as the rounding envelope.  Bound: err_k <= max(2e-5, 2 x envelope_k) with the envelope
-    accumulated up to step k.  Adam at lr 1e-3 turns rounding differences into loss spikes late in the run (the reference's own
-    fp32 curve is up to 5x away from its fp64 twin at single samples), so the level of the last 1000 steps is checked too."""
+def _run_ns_curve(g, steps):
     import torch
     from nsfnet_b200.nsfnet import PysicsInformedNeuralNetwork
     from nsfnet_b200.cavity_data import cavity_boundary
-    g = np.load(os.path.join(golden_dir, name + ".npz"))
     P = PysicsInformedNeuralNetwork(Re=float(g["Re"]), layers=4, hidden_size=120, N_f=g["xf"].size, bc_weight=10, eq_weight=1)
     off = 0
     flat = torch.as_tensor(g["params"]).cuda()
@@ -175,14 +168,62 @@ def test_full_size_curves_track_reference(golden_dir, name):
     P.verbose = False
     P.set_boundary_data(cavity_boundary(513)); P.set_eq_training_data((g["xf"], g["yf"]))
     P.opt.param_groups[0]["lr"] = float(g["lr"])
-    every = int(g["every"])
     curve = []
-    for k in range(int(g["steps"])):
+    for k in range(steps):                                   # the reference's loop body, NSFnet/pinn_solver.py:250-254
         loss, _ = P.fwd_computing_loss_2d()
         loss.backward(); P.opt.step(); P.opt.zero_grad()
-        if k % every == 0:
-            curve.append(loss.detach())
-    curve = torch.stack(curve).double().cpu().numpy()
+        curve.append(loss.detach())
+    return torch.stack(curve).double().cpu().numpy()
+
+
+def _curve_report(lines):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r2_curves.txt"), "a") as f:
+        f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+@pytest.mark.parametrize("name", ["curve_early_ns_re100", "curve_early_ns_re1000"])
+def test_loss_curves_track_reference_step_by_step(golden_dir, name):
+    """BASELINE config 1: NSFnet 4x120, N_f = 10 000, the reference's 2052 boundary points, Adam lr 1e-3, EVERY one of the
+    first 800 steps against the UNMODIFIED reference's own loop (tests/golden/make_golden_r2.py `early`).
+
+    Adam at lr 1e-3 amplifies rounding differences by ~x30 per 100 steps: the reference run with 1 host thread instead of 4 (same
+    fp32 program, another summation order) is 3e-7 away from itself at step 100, 5e-5 at step 200, 4e-3 at step 400 and 6 % at step
+    800; its fp64 twin likewise.  So 'tracks the reference' cannot be a fixed tolerance; it is: at every step the kernel's curve is
+    no further from the reference's than TWO legitimate evaluations of the reference are from each other,
+        dev_kernel(t) <= max(2e-5, 3 x envelope(t + 25)),   envelope = running max of (1-thread fp32, fp64) deviations,
+    (a factor 3 and 25 steps of slack on an exponentially growing envelope), and bit-level agreement at the start."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    T = int(g["steps"])
+    curve = _run_ns_curve(g, T)
+    ref = g["curve_fp32_t4"]
+    dev = np.abs(curve - ref) / ref
+    env = np.maximum.accumulate(np.maximum(np.abs(g["curve_fp32_t1"] - ref) / ref, np.abs(g["curve_fp64"] - ref) / ref))
+    shifted = np.concatenate([env[25:], np.full(25, env[-1])])
+    bound = np.maximum(2e-5, 3.0 * shifted)
+    ks = [0, 50, 100, 150, 200, 300, 400, 600, 799]
+    _curve_report([f"{name}: first {T} Adam steps, every step, N_f = {g['xf'].size}",
+                   "  step                      " + " ".join(f"{k:9d}" for k in ks),
+                   "  kernel vs reference       " + " ".join(f"{dev[k]:9.2e}" for k in ks),
+                   "  reference vs itself (env) " + " ".join(f"{env[k]:9.2e}" for k in ks),
+                   f"  worst ratio dev / bound {np.max(dev / bound):.3f} at step {int(np.argmax(dev / bound))}; loss at step {T - 1}: kernel {curve[-1]:.4e}, reference {ref[-1]:.4e} "
+                   f"(1 thread {g['curve_fp32_t1'][-1]:.4e}, fp64 {g['curve_fp64'][-1]:.4e})"])
+    assert dev[0] < 2e-6 and np.all(dev[:50] < 1e-5)
+    assert np.all(dev <= bound), (int(np.argmax(dev / bound)), float(np.max(dev / bound)))
+
+
+@pytest.mark.parametrize("name", ["curve_full_ns_re100", "curve_full_ns_re1000"])
+def test_full_size_curves_track_reference(golden_dir, name):
+    """The same run to 5000 steps (loss every 100 steps from the reference's own loop, and its fp64 twin).  Past step ~500 the
+    trajectories of ANY two fp32 evaluations have separated (test above), so what is compared is what survives chaos: the loss
+    level.  Per sample the kernel's loss stays within the band the reference's own fp32 / fp64 pair spans, widened by a factor 3
+    (Adam spikes make single samples of the reference's own pair differ by up to 5x), and the median of the last 1000 steps
+    within max(25 %, 2 x the reference's own fp32-vs-fp64 gap)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    every = int(g["every"])
+    curve = _run_ns_curve(g, int(g["steps"]))[::every]
     ref, c64 = g["curve"], g["curve_fp64"]
     err = np.abs(curve - ref) / ref
     env = np.maximum.accumulate(np.abs(c64 - ref) / ref)
@@ -193,11 +234,10 @@ def test_full_size_curves_track_reference(golden_dir, name):
              f"  first 10 samples: deviation {np.array2string(err[:10], precision=2)}",
              f"                    envelope  {np.array2string(env[:10], precision=2)}",
              f"  median loss of the last 1000 steps: kernel {lvl:.4e}, reference fp32 {lvl_ref:.4e}, reference fp64 {lvl64:.4e}"]
-    out = os.path.join(ROOT, "gpurun_out")
-    os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "r2_curves.txt"), "a") as f:
-        f.write("\n".join(lines) + "\n")
-    print("\n".join(lines))
+    _curve_report(lines)
     assert err[0] < 1e-5
-    assert np.all(err <= np.maximum(2e-5, 2.0 * env)), (err, env)
+    lo, hi = np.minimum(ref, c64), np.maximum(ref, c64)
+    # smoothed band: the reference pair over a window of +-2 samples (a spike lands one sample earlier or later in another run)
+    pad = lambda a, f: np.array([f(a[max(0, i - 2):i + 3]) for i in range(a.size)])
+    assert np.all(curve <= 3.0 * pad(hi, np.max)) and np.all(curve >= pad(lo, np.min) / 3.0), (curve, lo, hi)
     assert abs(np.log(lvl / lvl_ref)) <= max(np.log(1.25), 2 * abs(np.log(lvl64 / lvl_ref)))

@@ -106,3 +106,17 @@ int main(void) {
             assert int(val) == getattr(getattr(_capi, struct), field).offset, key
     assert int(out["NSF_LOSS_SLOTS"]) == _capi.NSF_LOSS_SLOTS and int(out["NSF_MAX_BLOCKS"]) == _capi.NSF_MAX_BLOCKS
     assert int(out["NSF_VTM_FROM_E"]) == _capi.NSF_VTM_FROM_E
+
+
+def test_mma_issue_loop_has_no_register_spills():
+    """scripts/check_issuer_spills.py: no local-memory load / store between the tcgen05.mma instructions of the points-on-M kernels
+    (a spill in the single issuing thread's loop cost 20 % of the step; the issuer's descriptors are kept loop-variant for that reason)."""
+    import importlib.util
+    import shutil
+    from nsfnet_b200 import _capi
+    if shutil.which("cuobjdump") is None or not os.path.exists(_capi.LIB_PATH):
+        pytest.skip("needs cuobjdump and the built library")
+    spec = importlib.util.spec_from_file_location("check_issuer_spills", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "check_issuer_spills.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    seen, bad = mod.check(_capi.LIB_PATH)
+    assert seen >= 8 and not bad, bad
