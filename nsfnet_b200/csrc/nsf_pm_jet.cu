@@ -54,7 +54,7 @@ namespace {
 // moves the gradient; that of the dgrad chains does not (a relative 1e-7 on the adjoints).  Forward stages therefore use NACC_F
 // accumulators (the weight-gradient accumulator is free then: all 512 columns), reverse stages NACC_R.
 #ifndef NSF_PM_NACC_F128
-#define NSF_PM_NACC_F128 4
+#define NSF_PM_NACC_F128 3
 #endif
 #ifndef NSF_PM_NACC_R128
 #define NSF_PM_NACC_R128 1
@@ -103,6 +103,9 @@ struct Cfg {
   static constexpr uint32_t MISC = MT == 128 ? 15360 : 12288;
   static constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;
   static_assert(H % 8 == 0 && KS % GK == 0 && H % CW == 0 && CW % 8 == 0 && NCH <= 5, "shape");
+  // Accumulator of k-step ks' hi * hi product when na accumulators share a contraction: the LAST accumulator (the corrections') takes exactly
+  // the last chunk's k-steps, so that its own hi * hi products follow every correction; the others share the rest evenly.
+  __host__ __device__ static constexpr int acc_of(int ks, int na) { return (na == 1 || ks >= KS - KPC) ? na - 1 : ks * (na - 1) / (KS - KPC); }
   static_assert(SMEM_BYTES <= 232448, "shared memory");
   static_assert(OFF_Q % 1024 == 0 && OFF_WHI % 1024 == 0 && PART % 1024 == 0, "swizzle phase");
 };
@@ -328,12 +331,16 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
         const uint32_t d_col = tmem + (fwd_stage ? DCOL_F : DCOL);
         long long t0 = 0, t1 = 0;
         const uint32_t a_hi = sb4 + (C::OFF_P >> 4) + lbo_field(C::GRP), a_lo = a_hi + (C::PART >> 4);
-        // The epilogue hands the operand image over chunk by chunk (CW neurons = KPC k-steps of this contraction): the two
-        // correction products of a k-step (lo * hi, hi * lo) are issued as soon as its neurons are written and run under the
-        // epilogue; the hi * hi products follow when the image is complete.  Corrections first on purpose: the tensor core
-        // TRUNCATES when it adds into the fp32 accumulator, so the 2^-11-sized terms go in while the accumulator is small
-        // (10 full-magnitude accumulations per layer instead of 30; interleaving the three products per k-step tripled the
-        // residual error and failed the 1e-5 bar on the EVM gradient).
+        // The epilogue hands the operand image over chunk by chunk (CW neurons = KPC k-steps of this contraction) and ALL three products
+        // of a k-step are issued as soon as its neurons are written, so that only the last chunk's MMAs are left when the epilogue
+        // finishes (a separate hi * hi pass after the hand-over left 10 - 15 MMAs, 600 - 900 cycles, exposed in every stage).
+        // The tensor core TRUNCATES when it adds into the fp32 accumulator, so what shares an accumulator matters (oracle/tc_model.py):
+        //   forward stages: the hi * hi products of k-step range a = ks NACC_F / KS go to accumulator a; the 2^-11-sized corrections
+        //   (lo * hi, hi * lo) of every k-step go to the LAST accumulator, whose own hi * hi products (the last chunk's) are issued
+        //   after all of them -- the small terms are in while that accumulator is small;
+        //   reverse stages: NACC_R accumulators likewise (1 by default: the rounding bias of the dgrad chains does not move the gradient).
+        const int na = fwd_stage ? C::NACC_F : C::NACC_R;
+        const uint32_t d_corr = d_col + (uint32_t)((na - 1) * C::NB);
         int ready_upto = -1;      // chunks [0, ready_upto] have been handed over
 #pragma unroll
         for (int c = 0; c < C::NCH; ++c) {
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
           }
           if (dbg) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
 #pragma unroll
-          for (int kc = 0; kc < C::KPC; ++kc) {
+          for (int kc = 0; kc < C::KPC; ++kc) {       // the chunk's corrections ...
             const int ks = c * C::KPC + kc, gi = ks / C::GK, kk = ks % C::GK;
             if (kk == 0) {
               if (dbg) t1 = clock64();
@@ -359,27 +366,25 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
             const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
             const uint32_t w_lo = sb4 + ((C::OFF_WLO + (gi & 1) * C::WBLK) >> 4) + lbo_field(128);
             const uint32_t da = (uint32_t)(ks * 1024) >> 4, dw = (kk * wsub) >> 4;
-            mma_tf32_elect2(d_col, a_lo + da, AHI, w_hi + dw, BHI, idesc, ks > 0, leader);
-            mma_tf32_elect2(d_col, a_hi + da, AHI, w_lo + dw, BHI, idesc, 1, leader);
+            mma_tf32_elect2(d_corr, a_lo + da, AHI, w_hi + dw, BHI, idesc, ks > 0, leader);
+            mma_tf32_elect2(d_corr, a_hi + da, AHI, w_lo + dw, BHI, idesc, 1, leader);
             if (kk == C::GK - 1) mma_commit_elect(&misc->lo_free[gi & 1], leader);
+          }
+#pragma unroll
+          for (int kc = 0; kc < C::KPC; ++kc) {       // ... then its hi * hi products (in the corrections' accumulator: after ALL corrections)
+            const int ks = c * C::KPC + kc, gi = ks / C::GK, kk = ks % C::GK;
+            const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
+            const uint32_t da = (uint32_t)(ks * 1024) >> 4, dw = (kk * wsub) >> 4;
+            // accumulator of this k-step's hi * hi product; it starts from zero unless it is the corrections' accumulator
+            const int ac = fwd_stage ? C::acc_of(ks, C::NACC_F) : C::acc_of(ks, C::NACC_R);
+            const int acp = ks == 0 ? -1 : (fwd_stage ? C::acc_of(ks - 1, C::NACC_F) : C::acc_of(ks - 1, C::NACC_R));
+            const bool fresh = ac != acp && ac != na - 1;
+            mma_tf32_elect2(d_col + (uint32_t)(ac * C::NB), a_hi + da, AHI, w_hi + dw, BHI, idesc, fresh ? 0 : 1, leader);
+            if (kk == C::GK - 1) mma_commit_elect(&misc->hi_free[gi], leader);
           }
           if (dbg) c_issue += clock64() - t0;
         }
         if (dbg) t0 = clock64();
-#pragma unroll
-        for (int gi = 0; gi < C::NG; ++gi) {
-          const uint32_t w_hi = sb4 + ((C::OFF_WHI + gi * C::WBLK) >> 4) + lbo_field(128);
-#pragma unroll
-          for (int kk = 0; kk < C::GK; ++kk) {
-            // accumulator 0 holds the corrections; the others start from zero with their first k-step
-            const int ks = gi * C::GK + kk;
-            const int ac = fwd_stage ? ks * C::NACC_F / C::KS : ks * C::NACC_R / C::KS;
-            const bool fresh = ac > 0 && (fwd_stage ? (ks - 1) * C::NACC_F / C::KS : (ks - 1) * C::NACC_R / C::KS) != ac;
-            const uint32_t da = (uint32_t)(ks * 1024) >> 4, dw = (kk * wsub) >> 4;
-            mma_tf32_elect2(d_col + (uint32_t)(ac * C::NB), a_hi + da, AHI, w_hi + dw, BHI, idesc, fresh ? 0 : 1, leader);
-          }
-          mma_commit_elect(&misc->hi_free[gi], leader);
-        }
         ready_ph ^= 1u;
         mma_commit_elect(&misc->dfull, leader);
         ++stage_ctr;
@@ -1008,7 +1013,7 @@ int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params,
   const int pts = nsf_pm_tile_points(g);
   a.n_tiles = (int)((k.n + pts - 1) / pts);
   {
-    static const int ho_env = [] { const char* v = getenv("NSF_PM_HO"); return v ? atoi(v) : 0x15; }();   // hand-over after chunks 0, 2, 4
+    static const int ho_env = [] { const char* v = getenv("NSF_PM_HO"); return v ? atoi(v) : 0x1d; }();   // hand-over after chunks 0, 2, 3, 4
     a.ho_mask = (ho_env & 0x1f) | 0x10;
   }
   a.dbg = (s->dbg_on && train) ? s->dbg : nullptr;
