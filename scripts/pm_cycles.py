@@ -24,5 +24,6 @@ tiles = c[3] / (2 * L - 1)
 print(f"{wl} n={n}: tiles/CTA {tiles:.0f}, MMA stages {c[3]:.0f}")
 print(f"issuer  per stage: wait-operands {c[0]/c[3]:.0f}  issue+weights {c[1]/c[3]:.0f}  (weight wait {c[2]/c[3]:.0f})   per tile total {(c[0]+c[1])/tiles:.0f}")
 print(f"epi w0 per tile: stage0 {c[12]/tiles:.0f}  fwd hidden {c[13]/tiles:.0f}  output+bwd {c[14]/tiles:.0f}  rev phase A {c[15]/tiles:.0f}  rev phase B {c[16]/tiles:.0f}  last {c[17]/tiles:.0f}   wait-D fwd {c[18]/tiles:.0f}  wait-D rev {c[19]/tiles:.0f}")
+print(f"epi wN per tile: stage0 {c[20]/tiles:.0f}  fwd hidden {c[21]/tiles:.0f}  output+bwd {c[22]/tiles:.0f}  rev phase A {c[23]/tiles:.0f}  rev phase B {c[24]/tiles:.0f}  last {c[25]/tiles:.0f}   wait-D fwd {c[26]/tiles:.0f}  wait-D rev {c[27]/tiles:.0f}")
 for nm, o in (("epi w0 ", 4), ("epi wN ", 8)):
     print(f"{nm} per tile: wait-D {c[o]/tiles:.0f}  wait-wgrad {c[o+1]/tiles:.0f}  work {c[o+2]/tiles:.0f}")
