@@ -503,7 +503,12 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
 #pragma unroll
         for (int c = 0; c < C::NCH; ++c)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) d[c][i] += (ac + 1 < NA) ? e[c][i] + f[c][i] : e[c][i];
+          for (int i = 0; i < 4; i += 2) {      // packed fp32x2 adds (sm_100): the same roundings, half the instructions
+            float2 s2 = make_float2(e[c][i], e[c][i + 1]);
+            if (ac + 1 < NA) s2 = __fadd2_rn(s2, make_float2(f[c][i], f[c][i + 1]));
+            const float2 r2 = __fadd2_rn(make_float2(d[c][i], d[c][i + 1]), s2);
+            d[c][i] = r2.x; d[c][i + 1] = r2.y;
+          }
       }
     };
     // dW_l (TMEM lane = output neuron j, column = input neuron k) of the tile -> added to this CTA's gradient row.  Every element
