@@ -25,6 +25,8 @@ static inline nsf_f4 nsf_ldcs4(const float* p) { return nsf_ld4(p); }
 static inline void nsf_st4(float* p, nsf_f4 v) { std::memcpy(p, &v, 16); }
 static inline void nsf_stcs4(float* p, nsf_f4 v) { nsf_st4(p, v); }
 static inline float nsf_ldg(const float* p) { return *p; }
+static inline void nsf_cp16(float* dst_smem, const float* src) { std::memcpy(dst_smem, src, 16); }
+static inline void nsf_cp_wait() {}
 static inline float nsf_tanh(float x) { return std::tanh(x); }
 static inline float nsf_fma(float a, float b, float c) { return std::fma(a, b, c); }
 #else
@@ -37,6 +39,11 @@ NSF_DEV nsf_f4 nsf_ldcs4(const float* p) { return __ldcs(reinterpret_cast<const 
 NSF_DEV void nsf_st4(float* p, nsf_f4 v) { *reinterpret_cast<float4*>(p) = v; }
 NSF_DEV void nsf_stcs4(float* p, nsf_f4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 NSF_DEV float nsf_ldg(const float* p) { return __ldg(p); }
+// 16 bytes global -> shared without a register round trip (LDGSTS); nsf_cp_wait: this thread's copies have landed
+NSF_DEV void nsf_cp16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+NSF_DEV void nsf_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 NSF_DEV float nsf_tanh(float x) { return nsf_tanh_fast(x); }
 NSF_DEV float nsf_fma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
@@ -59,6 +66,7 @@ struct NsfTile {
   float* ys;     // smem [PT]
   float* ov;     // smem [NS][4][PT]  network outputs, then their adjoints
   float* red;    // smem [PT][6]
+  float* wsm;    // smem [HP][HP]  (NS = 1) the weights of the next contraction, staged by nsf_ph_wstage
   float* stash;  // global, this CTA: [L][NS][HP][PT]
   float* grow;   // global, this CTA's gradient row
   long long p0;  // first point of the tile
@@ -154,8 +162,19 @@ NSF_DEV void nsf_ph_act(const NsfTile& c, NsfRegs<NS>& r, int tid, int l, bool d
   }
 }
 
+// ---- phase (NS = 1): the HP x HP weights of the next contraction, global -> shared memory ---------
+// The value-stream launches are small (a boundary block is 2052 points: ONE tile per CTA), so a CTA reads every weight exactly
+// once and the contraction loop below, fed through L1, ran at one L2 round trip per two k (170 us for the block, 11 % of a
+// 120 000-point training iteration).  Here all of a layer's loads are in flight at once (asynchronous copies, no registers),
+// beside the other work of the phase; nsf_cp_wait() before the phase's barrier.
+template <int NS, int PT>
+NSF_DEV void nsf_ph_wstage(const NsfTile& c, int tid, const float* W) {
+  const int HP = c.a->g.HP, n4 = HP * HP / 4;
+  for (int i = tid; i < n4; i += c.NT) nsf_cp16(c.wsm + 4 * i, W + 4 * i);
+}
+
 // ---- phase: acc[s][ji][pi] = sum_k src[s][k][p] * W[k][j]  (+ bias on stream 0) -----------------
-// W is row-major [k][HP] (Wt_l for the forward pass, W_l for dgrad), read through L1.
+// W is row-major [k][HP] (Wt_l for the forward pass, W_l for dgrad): NS = 4 reads it through L1, NS = 1 from the staged copy.
 template <int NS, int PT>
 NSF_DEV void nsf_ph_gemm(const NsfTile& c, NsfRegs<NS>& r, int tid, const float* src, const float* W, const float* bias) {
   constexpr int NPG = PT / 4;
@@ -171,10 +190,10 @@ NSF_DEV void nsf_ph_gemm(const NsfTile& c, NsfRegs<NS>& r, int tid, const float*
       for (int s = 1; s < NS; ++s) r.acc[s][ji][pi] = 0.f;
     }
   }
-  const float* wp = W + jg * 4;
+  const float* wp = (NS == 1 ? c.wsm : W) + jg * 4;
 #pragma unroll 2
   for (int k = 0; k < HP; ++k) {
-    const nsf_f4 w = nsf_ldg4(wp + (long long)k * HP);
+    const nsf_f4 w = NS == 1 ? nsf_ld4(wp + k * HP) : nsf_ldg4(wp + (long long)k * HP);
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       const nsf_f4 av = nsf_ld4(src + nsf_aoff<PT>(HP, s, k, pg));
@@ -557,6 +576,7 @@ NSF_DEV void nsf_cta_program(const NsfKernelArgs& a, float* smem, int bid, int n
   c.ys = c.xs + PT;
   c.ov = c.ys + PT;
   c.red = c.ov + NS * 4 * PT;
+  c.wsm = c.red + PT * 6;
   c.stash = a.stash ? a.stash + (long long)bid * a.stash_stride : (float*)0;
   c.grow = a.scratch ? a.scratch + (long long)bid * g.gs_row() : (float*)0;
   c.NT = nthreads;
@@ -568,10 +588,13 @@ NSF_DEV void nsf_cta_program(const NsfKernelArgs& a, float* smem, int bid, int n
     c.p0 = (long long)tile * PT;
     c.nvalid = (int)((a.n - c.p0) < PT ? (a.n - c.p0) : PT);
     NSF_PHASE(nsf_ph_load<NS, PT>(c, tid))
-    NSF_PHASE(nsf_ph_layer0<NS, PT>(c, r, tid); nsf_ph_act<NS, PT>(c, r, tid, 0, train))
+    // (NS = 1: the weights of a contraction are staged one phase ahead, beside work that does not touch the staging buffer)
+    NSF_PHASE(if (NS == 1 && g.L > 1) nsf_ph_wstage<NS, PT>(c, tid, a.pk + g.pk_wt(1));
+              nsf_ph_layer0<NS, PT>(c, r, tid); nsf_ph_act<NS, PT>(c, r, tid, 0, train); if (NS == 1) nsf_cp_wait())
     for (int l = 1; l < g.L; ++l) {
       NSF_PHASE(nsf_ph_gemm<NS, PT>(c, r, tid, c.act, a.pk + g.pk_wt(l), a.pk + g.pk_b(l)))
-      NSF_PHASE(nsf_ph_act<NS, PT>(c, r, tid, l, train))
+      NSF_PHASE(if (NS == 1 && l + 1 < g.L) nsf_ph_wstage<NS, PT>(c, tid, a.pk + g.pk_wt(l + 1));
+                nsf_ph_act<NS, PT>(c, r, tid, l, train); if (NS == 1) nsf_cp_wait())
     }
     NSF_PHASE(nsf_ph_out<NS, PT>(c, tid))
     if (mode == NSF_MODE_FWD) {
@@ -586,7 +609,8 @@ NSF_DEV void nsf_cta_program(const NsfKernelArgs& a, float* smem, int bid, int n
     if (!train) continue;
     NSF_PHASE(nsf_ph_outbwd<NS, PT>(c, r, tid))
     for (int l = g.L - 1; l >= 1; --l) {
-      NSF_PHASE(nsf_ph_zbar<NS, PT>(c, r, tid, l))
+      NSF_PHASE(if (NS == 1) nsf_ph_wstage<NS, PT>(c, tid, a.pk + g.pk_w(l));
+                nsf_ph_zbar<NS, PT>(c, r, tid, l); if (NS == 1) nsf_cp_wait())
       NSF_PHASE(nsf_ph_wgrad<NS, PT>(c, tid, l); nsf_ph_gemm<NS, PT>(c, r, tid, c.zb, a.pk + g.pk_w(l), (const float*)0))
     }
     NSF_PHASE(nsf_ph_zbar<NS, PT>(c, r, tid, 0))
@@ -601,5 +625,5 @@ NSF_DEV void nsf_cta_program(const NsfKernelArgs& a, float* smem, int bid, int n
 
 // floats of dynamic shared memory the program needs
 static inline long long nsf_ffma_smem_floats(int NS, int PT, int HP) {
-  return 2LL * NS * HP * PT + 2 * PT + NS * 4 * PT + PT * 6;
+  return 2LL * NS * HP * PT + 2 * PT + NS * 4 * PT + PT * 6 + (NS == 1 ? (long long)HP * HP : 0);
 }
