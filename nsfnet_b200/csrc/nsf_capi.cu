@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -427,8 +428,7 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
   };
 #ifndef NSF_EMU
   if (side) {
-    // fork: the blocks only need the packed image; they overlap the EVM forward and are joined before the persistent
-    // jet kernel starts (its CTAs need whole SMs: leftover block CTAs would delay them)
+    // fork: the blocks only need the packed image; they overlap the EVM forward and the start of the persistent jet kernel
     NSF_CUDA_OK(cudaEventRecord((cudaEvent_t)ctx->ev_fork, st));
     NSF_TRY(launch_blocks((cudaStream_t)ctx->side));
   }
@@ -456,11 +456,20 @@ extern "C" int nsf_step(NsfCtx* ctx, const float* params_main, const float* para
     a.resid_out = residuals_out; a.vis_t_out = vis_t_out;
     a.ebar_out = evm_train ? ctx->ebar_buf : nullptr;
 #ifndef NSF_EMU
-    if (side) NSF_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
+    // The blocks are joined BEHIND the jet kernel (before the gradient-row reduction).  Block CTAs still running when the jet kernel
+    // starts only hold back the jet CTAs with the highest indices -- the ones with one tile less whenever the tile count is not a
+    // multiple of the grid -- and at 10^6 points the blocks have long finished under the EVM forward.  Measured (scripts/ab_join.py):
+    // 1043 -> 1002 us per step at 120 000 points, 4064 -> 3974 at 500 000, no change at 10^6.  NSF_LATE_JOIN=0: join in front.
+    const char* lj = getenv("NSF_LATE_JOIN");
+    const bool late_join = !(lj && atoi(lj) == 0);
+    if (side && !late_join) NSF_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
 #endif
     NSF_TRY(time_mark(ctx, 0, st));
     NSF_TRY(launch_jet(ctx, a, params_main, &grids[0], st));
     NSF_TRY(time_mark(ctx, 1, st));
+#ifndef NSF_EMU
+    if (side && late_join) NSF_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_join, 0));
+#endif
   }
   if (!side) { NSF_TRY(launch_blocks(st)); }
   {
