@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   static_assert(C::DWN + C::NACC_R * C::NB <= 512 && C::NACC_F * C::NB <= 512, "tensor memory columns");
   extern __shared__ __align__(1024) uint8_t smem[];
   MiscT* misc = reinterpret_cast<MiscT*>(smem + C::OFF_MISC);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the eyes of the compiler: the role branches below are uniform branches
   const NsfNetGeom& g = a.g;
   constexpr int NMS = TRAIN ? 2 * L - 1 : L;          // MMA stages per tile
   constexpr uint32_t DCOL_F = 0;
