@@ -66,6 +66,14 @@ namespace {
 #ifndef NSF_PM_NACC_R64
 #define NSF_PM_NACC_R64 1
 #endif
+// Hand-over pattern: bit c set = the epilogue hands the operand image to the issuing warp after chunk c (the last chunk always).  Compile-time:
+// as a kernel argument the per-chunk branches cost 2 % of the kernel (6.79 -> 6.68 ms at hidden = 80).
+#ifndef NSF_PM_HO128
+#define NSF_PM_HO128 0x19
+#endif
+#ifndef NSF_PM_HO64
+#define NSF_PM_HO64 0x1b
+#endif
 // Issuing warps.  The MMA stages of a tile are dealt out round-robin over NISS warps that sit on different SM sub-partitions
 // (warp w is scheduled by sub-partition w & 3, which also runs the epilogue warps of TMEM quadrant w & 3).  One issuing warp
 // executes ~430 instructions per stage beside the ~625 of each of its scheduler's four epilogue warps: with a single issuer the
@@ -100,6 +108,7 @@ struct Cfg {
                                                  // tcgen05.ld fetches them all.  Neuron n = CW c + 4 w + i  <->  column WCOLS w + 4 c + i
                                                  // (the row order of the weight images: nsf_pm_pack_kernel)
   __host__ __device__ static constexpr int dcol(int n) { return WCOLS * ((n % CW) / 4) + 4 * (n / CW) + (n % 4); }
+  static constexpr int HO = MT == 128 ? NSF_PM_HO128 : NSF_PM_HO64;        // (measured over all patterns, scripts/build_variants.py: hidden 80 best with 0x19 = chunks 0, 3, 4; hidden 120 with 0x1b = 0, 1, 3, 4)
   static constexpr int NISS = MT == 128 ? NSF_PM_NISS128 : NSF_PM_NISS64;   // issuing warps (warps NEW .. NEW + NISS - 1), then the weight producer
   static constexpr int NEPI = NEW * 32;
   static constexpr int NTHREADS = (NEW + NISS + 1) * 32;
@@ -116,6 +125,7 @@ struct Cfg {
   static constexpr uint32_t MISC = MT == 128 ? 15360 : 12288;
   static constexpr uint32_t SMEM_BYTES = OFF_MISC + MISC;
   static_assert(H % 8 == 0 && KS % GK == 0 && H % CW == 0 && CW % 8 == 0 && NCH <= 5, "shape");
+  static_assert((HO >> (NCH - 1)) & 1, "the last chunk is always handed over");
   // Accumulator of k-step ks' hi * hi product when na accumulators share a contraction: the LAST accumulator (the corrections') takes exactly
   // the last chunk's k-steps, so that its own hi * hi products follow every correction; the others share the rest evenly.
   __host__ __device__ static constexpr int acc_of(int ks, int na) { return (na == 1 || ks >= KS - KPC) ? na - 1 : ks * (na - 1) / (KS - KPC); }
@@ -143,7 +153,6 @@ struct PArgs {
   float* scratch;        // gradient rows [grid][gs_row]
   int n_tiles;
   int zero;              // 0 at run time (keeps the issuer's descriptors loop-variant AND warp-uniform, see the issuer)
-  int ho_mask;           // bit c set: the epilogue hands the operand image over after chunk c (bit NCH-1 always set)
   long long* dbg;        // optional [grid][32] cycle counters
   int dbg_wa, dbg_wb;    // the two epilogue warps whose counters are recorded
 };
@@ -266,7 +275,7 @@ __device__ __forceinline__ void store_jet(uint32_t addr, const float v[4]) {
   sts4(addr + PART, lo[0], lo[1], lo[2], lo[3]);
 }
 
-template <int H, int L, int MT, bool TRAIN>
+template <int H, int L, int MT, bool TRAIN, bool DBG>
 __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(const PArgs a) {
   using C = Cfg<H, MT>;
   using MiscT = Misc<H, L, C::GWL_SMEM ? 4 : 0>;
@@ -281,8 +290,8 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   constexpr uint32_t DCOL_F = 0;
   constexpr uint32_t DCOL = C::DWN;                   // reverse stages: accumulators of NB columns behind the weight-gradient accumulator (columns [0, DWN))
   const uint32_t smem_base = smem_u32(smem);
-  const bool dbg = a.dbg != nullptr;
-  const int HO_MASK = a.ho_mask;
+  constexpr bool dbg = DBG;                           // cycle counters (nsf_get_stage_cycles): a separate instantiation, 6 % more instructions per stage
+  constexpr int HO_MASK = C::HO;
 
   if (warp == C::NEW) tmem_alloc(&misc->tmem_base, 512);
   if (tid == 0) {
@@ -531,7 +540,6 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
     // this worker's D cells of every chunk, the NA accumulators summed in fp32 (round to nearest), two accumulators per round trip
     auto load_d = [&](uint32_t base, auto na_tag, float (&d)[C::NCH][4]) {
       constexpr int NA = decltype(na_tag)::value;
-#pragma unroll
       ld_dall<MT, C::WCOLS, C::NCH>(base, d);
       if (NA == 1) tmem_ld_wait();
 #pragma unroll
@@ -939,21 +947,24 @@ struct PmState {
 
 typedef void (*PmKernel)(const PArgs);
 template <int H, int MT, int L>
-PmKernel pm_kernel_of(bool train) { return train ? nsf_pm_jet_kernel<H, L, MT, true> : nsf_pm_jet_kernel<H, L, MT, false>; }
-PmKernel pm_kernel(int H, int L, bool train) {
+PmKernel pm_kernel_of(bool train, bool dbg) {
+  if (!train) return nsf_pm_jet_kernel<H, L, MT, false, false>;
+  return dbg ? nsf_pm_jet_kernel<H, L, MT, true, true> : nsf_pm_jet_kernel<H, L, MT, true, false>;
+}
+PmKernel pm_kernel(int H, int L, bool train, bool dbg) {
   if (H == 80) {
     switch (L) {
-      case 2: return pm_kernel_of<80, 128, 2>(train);
-      case 3: return pm_kernel_of<80, 128, 3>(train);
-      case 4: return pm_kernel_of<80, 128, 4>(train);
-      case 5: return pm_kernel_of<80, 128, 5>(train);
-      default: return pm_kernel_of<80, 128, 6>(train);
+      case 2: return pm_kernel_of<80, 128, 2>(train, dbg);
+      case 3: return pm_kernel_of<80, 128, 3>(train, dbg);
+      case 4: return pm_kernel_of<80, 128, 4>(train, dbg);
+      case 5: return pm_kernel_of<80, 128, 5>(train, dbg);
+      default: return pm_kernel_of<80, 128, 6>(train, dbg);
     }
   }
   switch (L) {
-    case 2: return pm_kernel_of<120, 64, 2>(train);
-    case 3: return pm_kernel_of<120, 64, 3>(train);
-    default: return pm_kernel_of<120, 64, 4>(train);
+    case 2: return pm_kernel_of<120, 64, 2>(train, dbg);
+    case 3: return pm_kernel_of<120, 64, 3>(train, dbg);
+    default: return pm_kernel_of<120, 64, 4>(train, dbg);
   }
 }
 
@@ -992,8 +1003,8 @@ int nsf_pm_init(NsfCtx* ctx) {
     NSF_CUDA_OK(cudaMalloc((void**)&s->map, sizeof(int) * g.n_params));
     NSF_CUDA_OK(cudaMemcpy(s->map, map.data(), sizeof(int) * g.n_params, cudaMemcpyHostToDevice));
   }
-  for (int train = 0; train < 2; ++train)
-    NSF_CUDA_OK(cudaFuncSetAttribute(pm_kernel(g.H, g.L, train != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int v = 0; v < 3; ++v)
+    NSF_CUDA_OK(cudaFuncSetAttribute(pm_kernel(g.H, g.L, v != 0, v == 2), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ctx->ws_bytes += (long long)(wbytes + sbytes);
   ctx->pm = s;
   return NSF_OK;
@@ -1038,10 +1049,6 @@ int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params,
   const int pts = nsf_pm_tile_points(g);
   a.n_tiles = (int)((k.n + pts - 1) / pts);
   a.zero = 0;
-  {
-    static const int ho_env = [] { const char* v = getenv("NSF_PM_HO"); return v ? atoi(v) : 0x1d; }();   // hand-over after chunks 0, 2, 3, 4
-    a.ho_mask = (ho_env & 0x1f) | 0x10;
-  }
   a.dbg = (s->dbg_on && train) ? s->dbg : nullptr;
   {
     static const int wa = [] { const char* v = getenv("NSF_PM_DBG_WA"); return v ? atoi(v) : 0; }();
@@ -1052,7 +1059,7 @@ int nsf_pm_launch(NsfCtx* ctx, const NsfKernelArgs& k, const float* flat_params,
   if (grid <= 0) { *grid_out = 0; return NSF_OK; }
   const size_t smem = g.H == 80 ? Cfg<80, 128>::SMEM_BYTES : Cfg<120, 64>::SMEM_BYTES;
   const int nthreads = g.H == 80 ? Cfg<80, 128>::NTHREADS : Cfg<120, 64>::NTHREADS;
-  pm_kernel(g.H, g.L, train)<<<grid, nthreads, smem, st>>>(a);
+  pm_kernel(g.H, g.L, train, a.dbg != nullptr)<<<grid, nthreads, smem, st>>>(a);
   NSF_CUDA_OK(cudaGetLastError());
   ++*launches;
   s->last_grid = grid;

@@ -24,4 +24,4 @@ for i in range(12):
     if i >= 2:
         ms.append(abi.ctx.last_kernel_ms())
 import os
-print(f"{wl} n={n} path={path} HO={os.environ.get('NSF_PM_HO', 'default')}: kernel {np.median(ms):.3f} ms (min {min(ms):.3f})  -> {n / np.median(ms) / 1e3:.4g} pts/s")
+print(f"{wl} n={n} path={path} lib={os.path.basename(os.environ.get('NSF_B200_LIB', 'product'))}: kernel {np.median(ms):.3f} ms (min {min(ms):.3f})  -> {n / np.median(ms) / 1e3:.4g} pts/s")
