@@ -21,8 +21,8 @@
 // with every SM streaming) into NG "hi" slots (resident for the stage: read by the correction pass and by the main pass) and
 // two rotating "lo" slots.
 //
-// Warps: 4*NSUB epilogue warps (a warp may only touch TMEM lanes of quadrant warp & 3: 32 rows = 8 points x 4 streams), NISS
-// issuing warps taking the MMA stages in turn (tcgen05.mma / commit, one elected lane), one weight producer (one lane).  One tile is in flight per CTA:
+// Warps: 4*NSUB epilogue warps (a warp may only touch TMEM lanes of quadrant warp & 3: 32 rows = 8 points x 4 streams), one
+// issuer warp (tcgen05.mma / commit, one elected lane), one weight producer (one lane).  One tile is in flight per CTA:
 //   stage 0        : layer 0 (K = 2) on FFMA                                        -> P
 //   stage 1..L-1   : hidden layer forward, MMA -> D, epilogue: tanh jet             -> P (in place), stash (t, zx, zy, z_lap) to L2
 //   stage L        : output layer (N = 16), residuals, loss sums, adjoint seeds, output-layer dgrad / wgrad on FFMA -> P, Q
@@ -74,18 +74,6 @@ namespace {
 #ifndef NSF_PM_HO64
 #define NSF_PM_HO64 0x1b
 #endif
-// Issuing warps.  The MMA stages of a tile are dealt out round-robin over NISS warps that sit on different SM sub-partitions
-// (warp w is scheduled by sub-partition w & 3, which also runs the epilogue warps of TMEM quadrant w & 3).  One issuing warp
-// executes ~430 instructions per stage beside the ~625 of each of its scheduler's four epilogue warps: with a single issuer the
-// epilogue warps of quadrant 0 finished every stage 12 % later than the others (per-role cycle counters), and every stage ends
-// with its last warp.  A stage is issued by ONE thread, in order; the turn is passed on through an mbarrier.
-#ifndef NSF_PM_NISS128
-#define NSF_PM_NISS128 1
-#endif
-#ifndef NSF_PM_NISS64
-#define NSF_PM_NISS64 1
-#endif
-
 template <int H_, int MT_>
 struct Cfg {
   static constexpr int H = H_, MT = MT_;
@@ -109,9 +97,8 @@ struct Cfg {
                                                  // (the row order of the weight images: nsf_pm_pack_kernel)
   __host__ __device__ static constexpr int dcol(int n) { return WCOLS * ((n % CW) / 4) + 4 * (n / CW) + (n % 4); }
   static constexpr int HO = MT == 128 ? NSF_PM_HO128 : NSF_PM_HO64;        // (measured over all patterns, scripts/build_variants.py: hidden 80 best with 0x19 = chunks 0, 3, 4; hidden 120 with 0x1b = 0, 1, 3, 4)
-  static constexpr int NISS = MT == 128 ? NSF_PM_NISS128 : NSF_PM_NISS64;   // issuing warps (warps NEW .. NEW + NISS - 1), then the weight producer
   static constexpr int NEPI = NEW * 32;
-  static constexpr int NTHREADS = (NEW + NISS + 1) * 32;
+  static constexpr int NTHREADS = (NEW + 2) * 32;
   static constexpr uint32_t GRP = (H / 4) * 512; // one 32-row group of one image part
   static constexpr uint32_t PART = NQ * GRP;     // hi or lo
   static constexpr uint32_t IMG = 2 * PART;
@@ -164,7 +151,6 @@ struct Misc {
   uint64_t wdone[4];     // weight-gradient MMAs over row group q complete (P / Q rows of the group may be rewritten)
   uint64_t dwfree;       // the weight-gradient accumulator has been drained to the gradient row (one arrival per epilogue warp)
   uint64_t hi_full[3], hi_free[3], lo_full[2], lo_free[2];
-  uint64_t turn[4];      // turn[i]: the stage before issuing warp i's next one has been issued completely
   uint32_t tmem_base, pad;
   float loss[4][12];     // per TMEM quadrant: w eq1^2, w eq2^2, w eq3^2, w eq4^2, vis_t, count, gbL[0..2]
   float gb[4][L][H];     // bias gradients, one private copy per quadrant (single owner lane per entry: deterministic)
@@ -302,7 +288,6 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
     mbar_init(&misc->dwfree, C::NEW);
     for (int i = 0; i < 3; ++i) { mbar_init(&misc->hi_full[i], 1); mbar_init(&misc->hi_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&misc->lo_full[i], 1); mbar_init(&misc->lo_free[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&misc->turn[i], 1);
     mbar_fence_init();
   }
   {
@@ -326,37 +311,20 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
   const uint32_t tmem = misc->tmem_base;
   const int my_tiles = ((int)blockIdx.x < a.n_tiles) ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  constexpr int NISS = C::NISS;
-  constexpr int W_ISSUE = C::NEW, W_PROD = C::NEW + NISS;
-  static_assert(NISS >= 1 && NISS <= 4, "issuing warps");
-  if (warp >= W_ISSUE && warp < W_PROD) {
-    // =========================== issuing warps ===========================
-    // MMA stage n (counted over the CTA's tiles) is issued by warp n % NISS; every warp keeps all the phase counters.
-    const int me = warp - W_ISSUE;
+  constexpr int W_ISSUE = C::NEW, W_PROD = C::NEW + 1;
+  if (warp == W_ISSUE) {
+    // =========================== issuer warp ===========================
+    // (Dealing the MMA stages round-robin over 2 - 3 issuing warps on different schedulers was measured: the issuing warp's ~430 instructions per
+    // stage do share a scheduler with quadrant 0's epilogue warps, but passing the turn costs more -- 7.67 against 7.31 ms.)
     const uint32_t leader = elect_one();
     const uint32_t sb4_0 = smem_base >> 4;
-    uint32_t ready_ph = 0, stage_ctr = 0, lo_ctr0 = 0, lo_ctr1 = 0, wg_ctr = 0, turn_ph = 0;
-    int whose = 0;                       // issuing warp of the current stage
+    uint32_t ready_ph = 0, stage_ctr = 0, lo_ctr0 = 0, lo_ctr1 = 0, wg_ctr = 0;
     long long c_wait = 0, c_issue = 0, c_wwait = 0;
     constexpr uint32_t AHI = desc_hi_t(512, 1), BHI = desc_hi(256);
     for (int t = 0; t < my_tiles; ++t) {
 #pragma unroll 1
       for (int ms = 0; ms < NMS; ++ms) {
         const int s = ms + 1;
-        if (NISS > 1) {
-          const bool mine = whose == me;
-          whose = whose + 1 == NISS ? 0 : whose + 1;
-          if (!mine) {                   // another warp's stage: only the bookkeeping
-            ready_ph ^= 1u; ++stage_ctr; lo_ctr0 += (C::NG + 1) / 2; lo_ctr1 += C::NG / 2;
-            if (TRAIN && s > L) ++wg_ctr;
-            continue;
-          }
-          if (stage_ctr > 0) {           // every earlier stage has been issued (the MMAs stay in stage order, and every mbarrier this
-            mbar_wait_relaxed(&misc->turn[me], turn_ph, 32);    // stage waits on is at most one phase behind)
-            turn_ph ^= 1u;
-            tc_fence_after();
-          }
-        }
         const bool outst = (s == L);
         const uint32_t wsub = outst ? C::WSUB_O : C::WSUB;
         const uint32_t idesc = idesc_tf32(MT, outst ? 16 : C::NB, 1, 0);
@@ -447,18 +415,13 @@ __global__ void __launch_bounds__(Cfg<H, MT>::NTHREADS, 1) nsf_pm_jet_kernel(con
             mma_commit_elect(&misc->wdone[qq], leader);
           }
         }
-        if (NISS > 1) {                  // pass the turn on
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&misc->turn[me + 1 == NISS ? 0 : me + 1]);
-        }
         __syncwarp();
         if (dbg) c_issue += clock64() - t0;
       }
     }
-    if (dbg && lane == 0 && me == 0) {   // (warp 0's share, scaled: the issuing warps take equal turns)
+    if (dbg && lane == 0) {
       long long* d = a.dbg + (size_t)blockIdx.x * 32;
-      d[0] = c_wait * NISS; d[1] = c_issue * NISS; d[2] = c_wwait * NISS; d[3] = (long long)my_tiles * NMS;
+      d[0] = c_wait; d[1] = c_issue; d[2] = c_wwait; d[3] = (long long)my_tiles * NMS;
     }
   } else if (warp == W_PROD) {
     // =========================== weight producer (one lane) ===========================
