@@ -120,3 +120,5 @@ def test_mma_issue_loop_has_no_register_spills():
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
     seen, bad = mod.check(_capi.LIB_PATH)
     assert seen >= 8 and not bad, bad
+    # and the kernels are spill-free with uniform role branches (warp index through a shuffle; otherwise hundreds of R2UR)
+    assert not mod.check_uniform(_capi.LIB_PATH)
