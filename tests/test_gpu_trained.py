@@ -36,11 +36,14 @@ def _elem(a, truth):
 
 
 def _report(lines):
-    out = os.path.join(ROOT, "gpurun_out")
-    os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "r2_parity_trained.txt"), "a") as f:
-        f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    try:                                  # the record is a by-product: a read-only checkout must not fail the parity test
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r2_parity_trained.txt"), "a") as f:
+            f.write("\n".join(lines) + "\n")
+    except OSError:
+        pass
 
 
 def _check(name, path, o, g, n_eq, n, nb):
@@ -177,11 +180,14 @@ def _run_ns_curve(g, steps):
 
 
 def _curve_report(lines):
-    out = os.path.join(ROOT, "gpurun_out")
-    os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "r2_curves.txt"), "a") as f:
-        f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r2_curves.txt"), "a") as f:
+            f.write("\n".join(lines) + "\n")
+    except OSError:
+        pass
 
 
 @pytest.mark.parametrize("name", ["curve_early_ns_re100", "curve_early_ns_re1000"])
