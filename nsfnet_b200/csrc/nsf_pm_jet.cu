@@ -8,8 +8,8 @@
 //   MMA row   m = 4 * point + stream      (streams value, d/dx, d/dy, laplacian; M = 128 rows = 32 points)
 //   MMA col   n = output neuron           (N = H)
 //   forward / dgrad :  D[m, n] = sum_k A[m, k] * Wt[n, k]      A = activations / adjoints of the tile, B = the layer's weights
-//   weight gradient :  dW_l[j, k] += sum_m Zbar[m, j] * Act[m, k]   (contraction over the tile's rows, accumulators resident in
-//                                                                   tensor memory for the whole kernel, flushed every FLUSH tiles)
+//   weight gradient :  dW_l[j, k] += sum_m Zbar[m, j] * Act[m, k]   (contraction over the tile's rows; the accumulator lives for ONE tile and
+//                                                                   layer and is then added to the CTA's gradient row in L2: numerics, below)
 // One MMA now carries 32 points for 62 cycles (measured, scripts/probe_pm.cu) instead of 8 points for 43.
 //
 // Operand images of a tile (shared memory):  P (activations a_l going forward, adjoints zbar_l going back) and Q (a_{l-1}, the
